@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the SMC hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config 2 of BASELINE.json): bootstrap filter of the stochastic-volatility
+model (StochVol defaults), N = 1e7 particles per GPU, systematic resampling,
+ESSrmin = 0.5, observations = `np.random.seed(1); StochVol().simulate(1000)` (committed
+fixture; cycled if K > 1000).  One "step" = one filter step (propagate -> log-weight ->
+normalise/ESS -> resample if ESS < N/2) over all N particles; value = N * K / time.
+
+* `value`  : device-timed (CUDA events on the launching stream), particles resident
+             in HBM when the timed region starts;
+* `e2e`    : the same filter through the public API `particles_b200.SMC(...).run()`,
+             host observations in, host summaries out, wall clock around the call;
+* `roofline`: algorithmic bytes of the step kernel / its CUDA-event time, against
+             MEASURED_PEAKS.json `hbm_gbs`;
+* `cpu_baseline`: the oracle's NumPy restatement of the reference loop, timed on the
+             host cores of this box on a bounded sample (a few steps at N = 1e7).
+With --impl reference the CPU arm alone runs (all host cores, replicas as in multiSMC).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 10_000_000
+ESSRMIN = 0.5
+SCHEME = "systematic"
+HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def load_data(K):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_stats.npz"))
+    y = g["data/sv_seed1_T1000"]
+    reps = (K + len(y) - 1) // len(y)
+    return np.tile(y, reps)[:K].astype(np.float64)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            inside = t0 <= ts <= t1 + 0.1
+            try:
+                if inside:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:   # region shorter than one sample: use the closest samples
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle's NumPy restatement of particles.core.SMC (kind "port")
+# ---------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    n, steps, seed = args
+    from oracle import smc_numpy as orc
+    y = [np.atleast_1d(v) for v in load_data(steps + 1)]
+    np.random.seed(seed)
+    pf = orc.SMC(orc.Bootstrap(orc.StochVol(), y), N=n, resampling=SCHEME, ESSrmin=ESSRMIN)
+    pf.step()                                   # warm-up step (page faults, allocator)
+    t0 = time.perf_counter()
+    pf.run(nsteps=steps)
+    return time.perf_counter() - t0, pf.logLt
+
+
+def cpu_baseline(n, steps, workers=1):
+    """particle-steps/s of the NumPy port; `workers` independent filters in processes
+    (the reference's only parallelism is replica-level: utils.multiplexer / multiSMC)."""
+    t0 = time.perf_counter()
+    if workers == 1:
+        dt, _ = _cpu_worker((n, steps, 1))
+        wall = dt
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(workers) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(n, steps, 1 + i) for i in range(workers)])
+            wall = max(r[0] for r in res)
+    return workers * n * steps / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 16))            # ~1 GB of NumPy temporaries per worker at N=1e7
+    n = N_PER_GPU
+    K = max(1, min(args.steps, 4))              # bounded sample: ~3 s per step per worker
+    reps = max(1, min(args.warmup, 1))
+    for _ in range(reps):
+        cpu_baseline(n // 10, 1, 1)
+    value, wall = cpu_baseline(n, K, workers)
+    out = {
+        "impl": "reference", "metric": "particle-steps/sec (N x T), Bootstrap SV", "value": value,
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": reps,
+        "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"StochVol bootstrap N={n} systematic ESSrmin=0.5 (config 2), "
+                               f"{workers} replica filters in {workers} processes"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": workers, "kind": "port",
+                         "sample": f"{K} filter steps at N={n} per worker after 1 warm-up step; "
+                                   "oracle NumPy restatement of particles.core.SMC (the reference is "
+                                   "pure Python and cannot travel to this box)"},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    from particles_b200.core import _FusedEngine
+    if world > 1:
+        from particles_b200.parallel import ShardedFilter
+
+    K, W = args.steps, max(args.warmup, 3)
+    n = args.n
+    y = load_data(max(K, W))
+    fk = ssm.Bootstrap(ssm=ssm.StochVol(), data=[np.atleast_1d(v) for v in y[:K]])
+    spec = ssm.fused_spec(fk)
+
+    def make_engine(nsteps, seed):
+        sp = dict(spec)
+        sp["data"] = y[:nsteps].reshape(-1, 1).copy()
+        if world == 1:
+            return _FusedEngine(sp, n, SCHEME, ESSRMIN, seed)
+        return ShardedFilter(sp, n, SCHEME, ESSRMIN, seed, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W untimed steps on a throw-away filter (same kernels, same sizes)
+    wu = make_engine(W, 123)
+    wu.step(W)
+    torch.cuda.synchronize()
+    wu.close()
+
+    eng = make_engine(K, 2024)
+    launches0 = eng.ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record()
+    eng.step(K)                                   # EXACTLY K steps, no host sync inside
+    e1.record()
+    barrier()
+    tw1 = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = eng.ctx.launches - launches0
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    table = eng.summ.cpu().numpy()
+    n_rs = int(table[:, 2].sum())
+    logLt = float(table[K - 1, 1])
+    eng.close()
+
+    # per-kernel CUDA-event timing of the same K steps (separate pass, same kernels)
+    roof = None
+    if rank == 0 and world == 1:
+        eng2 = make_engine(K, 2024)
+        kms, kcnt = eng2.step_timed(K)
+        t2 = eng2.summ.cpu().numpy()
+        nrs2 = int(t2[:, 2].sum())
+        eng2.close()
+        peak, how = hbm_peak()
+        # algorithmic bytes of the step kernel: 32 B/particle on a non-resampling
+        # step (x, lw in; x', lw' out), 40 B on a resampling one (cdf in, A out, gather x, x', lw')
+        move_bytes = n * (32.0 * (K - 1 - nrs2) + 40.0 * nrs2)
+        move_ms = kms["move"]
+        ach = move_bytes / (move_ms * 1e-3) / 1e9
+        scan_gbs = (n * 16.0 * nrs2) / (kms["scan"] * 1e-3) / 1e9 if nrs2 else None
+        roof = {"bound": "hbm", "kernel": "k_move<StochVol,Bootstrap,systematic>",
+                "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None,
+                "avg_launch_us": 1e3 * move_ms / max(1, kcnt["move"]),
+                "algorithmic_bytes_per_particle": {"no_resample": 32, "resample": 40, "scan": 16},
+                "scan_kernel": {"achieved": scan_gbs, "launches_doing_work": nrs2,
+                                "ms_total_incl_noop_launches": kms["scan"]},
+                "share_of_step_time": {k: v / sum(kms.values()) for k, v in kms.items()}}
+
+    # end-to-end through the public API: host observations in, host summaries out
+    e2e = None
+    if world == 1:
+        y_host = [np.atleast_1d(v) for v in y[:K]]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y_host), N=n, resampling=SCHEME,
+                    ESSrmin=ESSRMIN, seed=77)
+        pf.run()
+        ll = pf.logLt                              # forces the device->host read of the result
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": n * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8,
+               "d2h_bytes_per_step": 32, "seconds": dt, "logLt": ll,
+               "api": "particles_b200.SMC(fk=Bootstrap(StochVol(), data), N).run()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, wall = cpu_baseline(n, 4, 1)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+               "sample": f"4 filter steps at N={n} after 1 warm-up step, single process "
+                         "(the reference runs one filter on one core); oracle NumPy restatement"}
+    total_n = n * world
+    out = {
+        "metric": "particle-steps/sec (N x T), Bootstrap SV", "value": total_n * K / (ms * 1e-3),
+        "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"StochVol bootstrap filter, N={n} particles per GPU "
+                               f"(global {total_n}), T={K}, systematic resampling, ESSrmin=0.5 "
+                               "(BASELINE config 2" + (")" if world == 1 else "/4, particle-sharded)"),
+                   "l2": "working set 4 x 80 MB of fp64 state per GPU > 126 MB L2 (no flush needed)",
+                   "resampling_steps": n_rs, "logLt": logLt,
+                   "parallelism": "single GPU" if world == 1 else f"particles sharded over {world} GPUs"},
+        "gpu_launches": launches,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

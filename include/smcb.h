@@ -1,0 +1,187 @@
+/* smcb.h -- C-ABI of libsmcb.so: the B200 (sm_100a) SMC inner loop.
+ *
+ * Drop-in boundary for the per-step hot path of nchopin/particles
+ * (particles.core.SMC: propagate -> log-weight -> normalise/ESS -> resample).
+ * The reference is pure Python with no FFI of its own; each entry point below
+ * names the reference function it replaces (paths relative to the reference
+ * root), and INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every array argument is a DEVICE pointer (fp64 / int64, contiguous) owned by
+ *    the caller (torch tensors in the Python host layer); scalars results are
+ *    written to device memory too, so no call synchronises the host;
+ *  - work is enqueued on the context's stream (smcb_set_stream);
+ *  - every function returns 0 on success, a negative SMCB_E* code otherwise,
+ *    with a message available from smcb_last_error();
+ *  - a context is bound to one device and is not thread-safe;
+ *  - results are deterministic: same inputs + same seed -> same bits, whatever
+ *    the grid size (all reductions and the scan use a fixed association order).
+ */
+#ifndef SMCB_H
+#define SMCB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB_OK 0
+#define SMCB_EINVAL (-1) /* bad argument (ValueError on the Python side)        */
+#define SMCB_ECUDA (-2)  /* CUDA runtime error                                   */
+#define SMCB_ENOSYS (-3) /* combination not implemented (NotImplementedError)    */
+
+typedef struct smcb_ctx smcb_ctx;
+
+const char *smcb_last_error(void);
+int smcb_version(void);
+
+/* one context per (device, stream); owns a small workspace + the Philox key */
+int smcb_create(smcb_ctx **out, int device, uint64_t seed);
+int smcb_destroy(smcb_ctx *ctx);
+int smcb_set_stream(smcb_ctx *ctx, void *cuda_stream);
+/* re-key the counter-based generator (replaces numpy.random.seed for this path) */
+int smcb_seed(smcb_ctx *ctx, uint64_t seed);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int64_t smcb_launch_count(const smcb_ctx *ctx);
+
+/* ---------------------------------------------------------------------------
+ * weights algebra  (particles/resampling.py)
+ * ------------------------------------------------------------------------- */
+
+/* Weights.__init__, resampling.py:217-226.  lw is modified in place (NaN -> -inf,
+ * line 220).  W_out may be NULL.  stats_out[4] = {max lw, log_mean, ESS, sum w}. */
+int smcb_normalise(smcb_ctx *ctx, double *lw, int64_t n, double *W_out, double *stats_out);
+
+#define SMCB_LSE_SUM 0  /* log_sum_exp   resampling.py:247-270            */
+#define SMCB_LSE_MEAN 1 /* log_mean_exp  resampling.py:291-317 (W optional) */
+#define SMCB_LSE_ESSL 2 /* essl          resampling.py:166-188            */
+int smcb_lse(smcb_ctx *ctx, int mode, const double *v, const double *W, int64_t n,
+             double *out);
+
+/* exp_and_normalise, resampling.py:138-163 */
+int smcb_exp_and_normalise(smcb_ctx *ctx, const double *lw, int64_t n, double *W_out);
+
+/* wmean_and_var, resampling.py:320-338; x is SoA (d, n); out = {mean[d], var[d]} */
+int smcb_wmean_and_var(smcb_ctx *ctx, const double *W, const double *x, int64_t n, int d,
+                       double *out);
+
+/* ---------------------------------------------------------------------------
+ * resampling  (particles/resampling.py)
+ * ------------------------------------------------------------------------- */
+#define SMCB_RS_MULTINOMIAL 0 /* resampling.py:540-558 */
+#define SMCB_RS_STRATIFIED 1  /* resampling.py:599-603 */
+#define SMCB_RS_SYSTEMATIC 2  /* resampling.py:606-610 */
+#define SMCB_RS_RESIDUAL 3    /* resampling.py:613-627 */
+
+/* Inclusive prefix sum of non-negative fp64 values (the CDF that inverse_cdf,
+ * resampling.py:484-509, walks).  Single pass, decoupled look-back with a
+ * fixed association order: deterministic and non-decreasing by construction. */
+int smcb_cumsum(smcb_ctx *ctx, const double *w, int64_t n, double *cdf_out);
+
+/* A[k] = min{ j : cdf[j] >= su[k] } clipped to n-1, for sorted su;
+ * == np.searchsorted(cdf, su, 'left') bit-exactly (inverse_cdf, resampling.py:484-509) */
+int smcb_searchsorted(smcb_ctx *ctx, const double *cdf, int64_t n, const double *su,
+                      int64_t m, int64_t *A_out);
+
+/* rs.resampling(scheme, W, M), resampling.py:464-481, 540-627.
+ * u_in (device) = the uniforms to use, in the order the reference draws them
+ * (systematic 1, stratified m, multinomial m+1, residual m+1); NULL -> Philox.
+ * scratch: at least smcb_resample_scratch_doubles(n, m) doubles.
+ * su_out / cdf_out may be NULL. */
+int64_t smcb_resample_scratch_doubles(int64_t n, int64_t m);
+int smcb_resample(smcb_ctx *ctx, int scheme, const double *W, int64_t n, int64_t m,
+                  int64_t *A_out, const double *u_in, double *scratch);
+
+/* Xp = X[A]  (core.py:332); X is SoA (d, n), Xp is SoA (d, m) */
+int smcb_gather(smcb_ctx *ctx, const double *X, int64_t n, const int64_t *A, int64_t m,
+                int d, double *Xp);
+/* same for row-major (n, d) particles, the layout user closures index as xp[:, i] */
+int smcb_gather_rows(smcb_ctx *ctx, const double *X, int64_t n, const int64_t *A, int64_t m,
+                     int d, double *Xp);
+
+/* ---------------------------------------------------------------------------
+ * distributions  (particles/distributions.py)
+ * an array argument may be NULL, in which case the scalar next to it is used
+ * ------------------------------------------------------------------------- */
+/* Normal.rvs, distributions.py:270-271; z_in = injected N(0,1) draws or NULL */
+int smcb_normal_rvs(smcb_ctx *ctx, const double *loc, double loc0, const double *scale,
+                    double scale0, const double *z_in, double *out, int64_t n);
+/* Normal.logpdf, distributions.py:273-274 */
+int smcb_normal_logpdf(smcb_ctx *ctx, const double *x, double x0, const double *loc,
+                       double loc0, const double *scale, double scale0, double *out,
+                       int64_t n);
+/* MvNormal.rvs / logpdf, distributions.py:946-969; SoA (d, n); L = host (d,d) lower
+ * Cholesky factor of cov, row-major; loc/scale: array (d, n), or NULL + host vector[d] */
+int smcb_mvnormal_rvs(smcb_ctx *ctx, const double *loc, const double *loc0,
+                      const double *scale, const double *scale0, const double *L, int d,
+                      const double *z_in, double *out, int64_t n);
+int smcb_mvnormal_logpdf(smcb_ctx *ctx, const double *x, const double *loc,
+                         const double *loc0, const double *scale, const double *scale0,
+                         const double *L, int d, double *out, int64_t n);
+/* standard normals / uniforms from the context's Philox stream */
+int smcb_standard_normal(smcb_ctx *ctx, double *out, int64_t n);
+int smcb_uniform(smcb_ctx *ctx, double *out, int64_t n);
+
+/* ---------------------------------------------------------------------------
+ * fused filter: the whole step of core.py:369-383 for a recognised model
+ * ------------------------------------------------------------------------- */
+#define SMCB_FK_BOOTSTRAP 0 /* state_space_models.py:299-349 */
+#define SMCB_FK_GUIDED 1    /* state_space_models.py:352-398 */
+#define SMCB_FK_APF 2       /* state_space_models.py:406-428 */
+#define SMCB_FK_AUXBOOT 3   /* state_space_models.py:431-438 */
+
+#define SMCB_MODEL_STOCHVOL 0      /* state_space_models.py:446-498             */
+#define SMCB_MODEL_LINGAUSS 1      /* kalman.py:397-452 (also README ToySSM)    */
+#define SMCB_MODEL_GORDON 2        /* state_space_models.py:546-577             */
+#define SMCB_MODEL_THETALOGISTIC 3 /* state_space_models.py:657-689             */
+#define SMCB_MODEL_BEARINGS 4      /* state_space_models.py:580-608 (d = 4)     */
+#define SMCB_MODEL_MVLINGAUSS 5    /* kalman.py:296-394 (d <= 8)                */
+#define SMCB_MODEL_DISCRETECOX 6   /* state_space_models.py:611-630             */
+#define SMCB_MODEL_STOCHVOLLEV 7   /* state_space_models.py:501-543             */
+
+#define SMCB_MAX_PARAMS 256
+#define SMCB_SUMMARY_STRIDE 4 /* per step: ESS, logLt, rs_flag, log_mean_w */
+
+typedef struct smcb_filter smcb_filter;
+
+typedef struct {
+    int32_t model, fk, scheme, dim;  /* dim = state dimension d                     */
+    int32_t dy, n_params, reserved0, reserved1;
+    int64_t n;                       /* particles on this device                    */
+    int64_t n_global;                /* particles over all ranks (== n if 1 GPU)    */
+    int64_t index_offset;            /* global index of local particle 0 (Philox)   */
+    int64_t T;                       /* number of data points                       */
+    double essrmin;
+    uint64_t seed;
+    double params[SMCB_MAX_PARAMS];  /* model constants, layout per model */
+    /* device buffers, all caller-owned */
+    double *X[2];      /* ping-pong state, SoA (d, n)                               */
+    double *lw[2];     /* ping-pong log-weights (n)                                 */
+    int64_t *A;        /* ancestors of the last resampling step (n)                 */
+    double *cdf;       /* (n) scratch: CDF of the last resampling step              */
+    double *data;      /* (T, dy) observations                                      */
+    double *summaries; /* (T, SMCB_SUMMARY_STRIDE)                                  */
+    const double *z_in; /* NULL, or injected N(0,1): (T, n_noise, n)                */
+    const double *u_in; /* NULL, or injected uniforms: (T, n + 1)                   */
+    double *scratch;    /* NULL, or n + 2 doubles (multinomial: exponential spacings) */
+    const double *step_consts; /* NULL, or (T) host-computed per-step model constants */
+} smcb_filter_desc;
+
+int smcb_filter_create(smcb_ctx *ctx, const smcb_filter_desc *desc, smcb_filter **out);
+int smcb_filter_destroy(smcb_filter *f);
+/* enqueue nsteps steps of SMC.__next__ (core.py:369-383); no host sync */
+int smcb_filter_step(smcb_filter *f, int64_t nsteps);
+/* same, with a CUDA-event pair around every kernel launch; synchronises at the end.
+ * out[0..3] = summed device ms of {init, weight-scan, spacings-scan, move} kernels,
+ * out[4..7] = launches of each (bench.py "roofline") */
+int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *out8);
+/* host-visible snapshot (synchronises the stream):
+ * out[0]=t, [1]=cur buffer index, [2]=rs_flag of last step, [3]=logLt, [4]=ESS,
+ * [5]=log_mean_w, [6]=max lw, [7]=sum w */
+int smcb_filter_state(smcb_filter *f, double *out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB_H */

@@ -1,0 +1,405 @@
+"""``SMC`` and ``FeynmanKac``: the step loop of ``particles/core.py:108-409`` on a B200.
+
+``SMC(fk=..., N=..., resampling=..., ESSrmin=..., collect=...)`` keeps the reference's
+constructor, iterator protocol and attributes (``t, X, Xp, A, wgts, aux, W, logLt,
+loglt, log_mean_w, rs_flag, cpu_time, summaries``).  Two execution paths:
+
+* FUSED (stock models recognised by ``state_space_models.fused_spec``): the whole
+  step -- ESS test, scan + search + gather, propagate, log-weight, max-shifted
+  normalisation, logLt recursion -- runs in libsmcb's kernels with the decision taken
+  on the device; ``run()`` enqueues all T steps without a host sync and reads the
+  (T, 4) summary table once.
+* PLUGIN (any other ``FeynmanKac``): the reference's loop (core.py:299-383) with the
+  model's ``M0 / M / logG / logeta`` called on CUDA tensors and our
+  ``resampling`` / ``Weights`` kernels underneath.
+
+There is no CPU path: without the CUDA library / device the constructor raises.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import collectors
+from . import resampling as rs
+from .device import as_device, context, empty, ptr, require_cuda
+
+
+class FeynmanKac:
+    """Abstract Feynman-Kac model -- particles/core.py:108-197."""
+
+    def __init__(self, T):
+        self.T = T
+
+    def _error_msg(self, meth):
+        return f"method/property {meth} missing in class {self.__class__.__name__}"
+
+    def M0(self, N):
+        raise NotImplementedError(self._error_msg("M0"))
+
+    def M(self, t, xp):
+        raise NotImplementedError(self._error_msg("M"))
+
+    def logG(self, t, xp, x):
+        raise NotImplementedError(self._error_msg("logG"))
+
+    @property
+    def isAPF(self):
+        return "logeta" in dir(self)
+
+    def done(self, smc):
+        return smc.t >= self.T
+
+    def time_to_resample(self, smc):
+        return smc.aux.ESS < smc.N * smc.ESSrmin          # strict <, core.py:183
+
+    def default_moments(self, W, X):
+        return rs.wmean_and_var(W, X)
+
+    def summary_format(self, smc):
+        return "t=%i: resample:%s, ESS (end of iter)=%.2f" % (smc.t, smc.rs_flag, smc.wgts.ESS)
+
+
+def _is_apf(fk):
+    return fk.isAPF if hasattr(fk, "isAPF") else ("logeta" in dir(fk))
+
+
+class _FusedEngine:
+    """Owns the device buffers of one fused filter and the smcb_filter handle."""
+
+    def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0):
+        self.ctx = context()
+        self.lib = self.ctx.lib
+        self.N, self.T = int(N), int(spec["data"].shape[0])
+        n, T = self.N, self.T
+        dev = self.ctx.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.X = [torch.empty(n, **f64), torch.empty(n, **f64)]
+        self.lw = [torch.empty(n, **f64), torch.empty(n, **f64)]
+        self.A = torch.empty(n, dtype=torch.int64, device=dev)
+        self.cdf = torch.empty(n, **f64)
+        self.summ = torch.zeros((T, _lib.SUMMARY_STRIDE), **f64)
+        # the observations are the only per-run host input of this path: pinned -> device
+        self.data_host = torch.from_numpy(spec["data"].reshape(-1)).pin_memory()
+        self.data = self.data_host.to(dev, non_blocking=True)
+        self.sc = None
+        if spec.get("step_consts") is not None:
+            self.sc = as_device(spec["step_consts"])
+        self.scratch = torch.empty(n + 2, **f64) if scheme == "multinomial" else None
+        self.z_in = self.u_in = None
+        if noise is not None:
+            z, u = noise
+            self.z_in = None if z is None else as_device(z)
+            self.u_in = None if u is None else as_device(u)
+        d = _lib.FilterDesc()
+        d.model, d.fk, d.scheme, d.dim = spec["model"], spec["fk"], _lib.RS_CODES[scheme], 1
+        d.dy, d.n_params = 1, len(spec["params"])
+        d.n, d.n_global = n, int(n_global or n)
+        d.index_offset, d.T = int(index_offset), T
+        d.essrmin, d.seed = float(ESSrmin), int(seed) & (2 ** 64 - 1)
+        for i, v in enumerate(spec["params"]):
+            d.params[i] = float(v)
+        d.X[0], d.X[1] = self.X[0].data_ptr(), self.X[1].data_ptr()
+        d.lw[0], d.lw[1] = self.lw[0].data_ptr(), self.lw[1].data_ptr()
+        d.A, d.cdf = self.A.data_ptr(), self.cdf.data_ptr()
+        d.data, d.summaries = self.data.data_ptr(), self.summ.data_ptr()
+        d.z_in = self.z_in.data_ptr() if self.z_in is not None else None
+        d.u_in = self.u_in.data_ptr() if self.u_in is not None else None
+        d.scratch = self.scratch.data_ptr() if self.scratch is not None else None
+        d.step_consts = self.sc.data_ptr() if self.sc is not None else None
+        self.desc = d
+        h = C.c_void_p()
+        _lib.check(self.lib.smcb_filter_create(self.ctx.handle, C.byref(d), C.byref(h)))
+        self.handle = h
+
+    def step(self, nsteps=1):
+        self.ctx.bind_stream()
+        _lib.check(self.lib.smcb_filter_step(self.handle, int(nsteps)))
+
+    def step_timed(self, nsteps):
+        """smcb_filter_step_timed: per-kernel device milliseconds (CUDA events)."""
+        self.ctx.bind_stream()
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.smcb_filter_step_timed(self.handle, int(nsteps), out))
+        ms = dict(zip(("init", "scan", "spacings", "move"), out[0:4]))
+        cnt = dict(zip(("init", "scan", "spacings", "move"), (int(v) for v in out[4:8])))
+        return ms, cnt
+
+    def state(self):
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.smcb_filter_state(self.handle, out))
+        return list(out)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.smcb_filter_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SMC:
+    """Drop-in for ``particles.SMC`` (particles/core.py:200-409).
+
+    Extra keyword arguments (all optional, defaults keep the reference's behaviour):
+    ``seed`` re-keys the device generator for this run; ``fused=False`` forces the
+    plugin path; ``noise=(z, u)`` injects standard normals / uniforms (parity tests).
+    """
+
+    def __init__(self, fk=None, N=100, qmc=False, resampling="systematic", ESSrmin=0.5,
+                 store_history=False, verbose=False, collect=None, seed=None, fused=None,
+                 noise=None):
+        require_cuda()
+        _lib.load()
+        if qmc:
+            raise NotImplementedError("SQMC (qmc=True) is outside the accelerated path")
+        if store_history is not False:
+            raise NotImplementedError("store_history is not available on the device path yet")
+        if resampling not in rs.rs_funcs:
+            raise ValueError(f"{resampling} is not a valid resampling scheme")
+        self.fk, self.N, self.qmc = fk, N, qmc
+        self.resampling, self.ESSrmin, self.verbose = resampling, ESSrmin, verbose
+        self.t = 0
+        self._done = 0        # completed steps (== t outside of a step; collectors see t = index)
+        self.cpu_time = None
+        self.hist = None
+        self.summaries = None if collect == "off" else collectors.Summaries(collect)
+        self._seed = np.random.randint(0, 2 ** 31 - 1) if seed is None else int(seed)
+        self._engine = None
+        self._noise = noise
+        spec = None
+        if fused is not False:
+            from .state_space_models import fused_spec
+            spec = fused_spec(fk)
+            if spec is not None and resampling == "residual":
+                spec = None                      # residual is not fused: plugin path
+            if spec is None and fused is True:
+                raise NotImplementedError("this Feynman-Kac model has no fused kernel")
+        if spec is not None:
+            self._engine = _FusedEngine(spec, N, resampling, ESSrmin, self._seed, noise)
+            self._row_cache = {}
+        else:
+            context().seed(self._seed)
+            self._p = {"rs_flag": False, "logLt": 0.0, "wgts": rs.Weights(), "aux": None,
+                       "X": None, "Xp": None, "A": None}
+
+    # ------------------------------------------------------------------ fused
+    @property
+    def fused(self):
+        return self._engine is not None
+
+    def _row(self, t):
+        """(ESS, logLt, rs_flag, log_mean_w) of step t from the device table."""
+        if t not in self._row_cache:
+            self._row_cache = {t: self._engine.summ[t].cpu().numpy()}
+        return self._row_cache[t]
+
+    def _cur(self):
+        return (self._done - 1) & 1      # step s writes buffers [s & 1]
+
+    # ------------------------------------------------------------- attributes
+    @property
+    def X(self):
+        if not self.fused:
+            return self._p["X"]
+        return None if self._done == 0 else self._engine.X[self._cur()]
+
+    @X.setter
+    def X(self, v):
+        self._p["X"] = v
+
+    @property
+    def rs_flag(self):
+        if not self.fused:
+            return self._p["rs_flag"]
+        return False if self._done == 0 else bool(self._row(self._done - 1)[2])
+
+    @property
+    def logLt(self):
+        if not self.fused:
+            return self._p["logLt"]
+        return 0.0 if self._done == 0 else float(self._row(self._done - 1)[1])
+
+    @property
+    def log_mean_w(self):
+        if not self.fused:
+            return self._p["log_mean_w"]
+        return float(self._row(self._done - 1)[3])
+
+    @property
+    def loglt(self):
+        if not self.fused:
+            return self._p["loglt"]
+        t = self._done - 1
+        if t == 0 or self.rs_flag:
+            return self.log_mean_w
+        return self.log_mean_w - float(self._engine.summ[t - 1, 3].item())
+
+    @property
+    def A(self):
+        if not self.fused:
+            return self._p["A"]
+        if self._done <= 1:
+            return None
+        if self.rs_flag:
+            return self._engine.A
+        return torch.arange(self.N, device=self._engine.A.device)      # core.py:335
+
+    @property
+    def Xp(self):
+        if not self.fused:
+            return self._p["Xp"]
+        if self._done <= 1:
+            return None
+        prev = self._engine.X[self._cur() ^ 1]
+        if not self.rs_flag:
+            return prev
+        out = torch.empty_like(prev)
+        ctx = self._engine.ctx
+        _lib.check(ctx.lib.smcb_gather(ctx.handle, ptr(prev), self.N, ptr(self._engine.A), self.N, 1,
+                                       ptr(out)))
+        return out
+
+    @property
+    def wgts(self):
+        if not self.fused:
+            return self._p["wgts"]
+        if self._done == 0:
+            return rs.Weights()
+        st = self._engine.state()
+        stats = torch.tensor([st[6], st[5], st[4], st[7]], dtype=torch.float64,
+                             device=self._engine.lw[0].device)
+        return rs.Weights._from_device_stats(self._engine.lw[self._cur()], stats)
+
+    @property
+    def aux(self):
+        if not self.fused:
+            return self._p["aux"]
+        return self.wgts
+
+    @property
+    def W(self):
+        return self.wgts.W
+
+    def __str__(self):
+        return self.fk.summary_format(self)
+
+    # ----------------------------------------------------------- plugin path
+    def reset_weights(self):                                  # core.py:299-305
+        p = self._p
+        if _is_apf(self.fk):
+            lw = rs.log_mean_exp(self.logetat, W=p["wgts"].W) - self._gather(self.logetat, p["A"])
+            p["wgts"] = rs.Weights(lw=lw)
+        else:
+            p["wgts"] = rs.Weights()
+
+    def setup_auxiliary_weights(self):                        # core.py:307-313
+        p = self._p
+        if _is_apf(self.fk):
+            self.logetat = as_device(self.fk.logeta(self.t - 1, p["X"]))
+            p["aux"] = p["wgts"].add(self.logetat)
+        else:
+            p["aux"] = p["wgts"]
+
+    def _gather(self, X, A):
+        ctx = context()
+        X = as_device(X)
+        d = 1 if X.ndim == 1 else X.shape[1]
+        out = torch.empty((A.shape[0],) + tuple(X.shape[1:]), dtype=X.dtype, device=X.device)
+        _lib.check(ctx.lib.smcb_gather_rows(ctx.handle, ptr(X), X.shape[0], ptr(A), A.shape[0], d,
+                                            ptr(out)))
+        return out
+
+    def generate_particles(self):                             # core.py:315-321
+        self._p["X"] = self.fk.M0(self.N)
+
+    def reweight_particles(self):                             # core.py:323-324
+        p = self._p
+        p["wgts"] = p["wgts"].add(self.fk.logG(self.t, p["Xp"], p["X"]))
+
+    def resample_move(self):                                  # core.py:326-337
+        p = self._p
+        p["rs_flag"] = bool(self.fk.time_to_resample(self))
+        if p["rs_flag"]:
+            p["A"] = rs.resampling(self.resampling, p["aux"].W, M=self.N)
+            p["Xp"] = self._gather(p["X"], p["A"])
+            self.reset_weights()
+        else:
+            p["A"] = torch.arange(self.N, device="cuda")
+            p["Xp"] = p["X"]
+        p["X"] = self.fk.M(self.t, p["Xp"])
+
+    def compute_summaries(self):                              # core.py:351-367
+        p = self._p
+        if self.t > 0:
+            prec = p["log_mean_w"]
+        p["log_mean_w"] = p["wgts"].log_mean
+        if self.t == 0 or p["rs_flag"]:
+            p["loglt"] = p["log_mean_w"]
+        else:
+            p["loglt"] = p["log_mean_w"] - prec
+        p["logLt"] += p["loglt"]
+        if self.verbose:
+            print(self)
+        if self.summaries:
+            self.summaries.collect(self)
+
+    # -------------------------------------------------------------- iterator
+    def __next__(self):
+        """One step of a particle filter (core.py:369-383)."""
+        if self.fk.done(self):
+            raise StopIteration
+        if self.fused:
+            self._engine.step(1)
+            self._done += 1
+            if self.verbose:
+                print(self)
+            if self.summaries:
+                self.summaries.collect(self)      # smc.t is still the index of this step
+            self.t += 1
+            return
+        if self.t == 0:
+            self.generate_particles()
+        else:
+            self.setup_auxiliary_weights()
+            self.resample_move()
+        self.reweight_particles()
+        self.compute_summaries()
+        self.t += 1
+        self._done = self.t
+
+    def next(self):
+        return self.__next__()
+
+    def __iter__(self):
+        return self
+
+    def run(self):
+        """Run until completion (core.py:391-409); ``cpu_time`` is the wall time of this
+        call, device work included (utils.timer semantics, utils.py:81-89)."""
+        t0 = time.perf_counter()
+        if self.fused and not self.verbose and (self.summaries is None or self.summaries.only_defaults) \
+                and type(self.fk).done is FeynmanKac.done:
+            T = self._engine.T
+            first = self.t
+            if first < T:
+                self._engine.step(T - first)
+                self.t = self._done = T
+            table = self._engine.summ.cpu().numpy()       # the one device->host read of the run
+            self._row_cache = {T - 1: table[T - 1]}
+            if self.summaries is not None:
+                self.summaries._extend_defaults([float(v) for v in table[first:T, 0]],
+                                                [float(v) for v in table[first:T, 1]],
+                                                [bool(v) for v in table[first:T, 2]])
+        else:
+            for _ in self:
+                pass
+            if self.fused:
+                torch.cuda.synchronize()
+        self.cpu_time = time.perf_counter() - t0

@@ -1,0 +1,634 @@
+// smcb_filter.cu -- the fused SMC step (particles/core.py:369-383) for the 1-D
+// Normal-kernel model family: one step = at most two kernels and no host sync.
+//
+//   k_scan_w   (resampling steps only; exits at once otherwise)
+//       W_i = exp(lw_i - m)/s computed on the fly  ->  inclusive scan  ->  cdf      16 B/particle
+//   k_move
+//       resampling step:  su_k -> A_k = search(cdf) -> xp = X[A_k] -> x' ~ M_t(xp)
+//                         -> lw' = logG  -> (max, sum exp, sum exp^2) partials        40 B/particle
+//       otherwise:        xp = X_k -> x' -> lw' = lw + logG -> partials               32 B/particle
+//       the block that retires last merges the partials in a fixed order and performs
+//       compute_summaries (core.py:351-367) and the ESS test of the NEXT step
+//       (core.py:181-183) on the device.
+//
+// The resample / no-resample decision, t, the ping-pong index and logLt live in a small
+// device struct (FilterDev), so the launch arguments are identical for every step.
+#include <string.h>
+
+#include <new>
+
+#include "smcb_common.cuh"
+#include "smcb_models.cuh"
+#include "smcb_reduce.cuh"
+#include "smcb_scan.cuh"
+#include "smcb_search.cuh"
+
+using namespace smcb;
+
+namespace smcb {
+
+struct FilterDev {
+    long long t;          // next step to run
+    int cur;              // X[cur], lw[cur] hold the particles of step t-1
+    int rs_flag;          // decision for step t, taken at the end of step t-1
+    int last_rs;          // rs_flag of the step just completed
+    int pad;
+    double logLt, log_mean_w, ess;
+    double wm, ws, wq;    // (max, sum exp, sum exp^2) of the inferential weights
+    double am, as, aq;    // same for the auxiliary weights (APF); == w* otherwise
+    double reset_c;       // APF: log_mean_exp(logetat, W), core.py:302
+};
+
+struct FilterArgs {
+    double *X[2];
+    double *lw[2];
+    long long *A;
+    double *cdf;
+    double *su;           // multinomial: z = cumsum(-log u), (n + 1)
+    const double *data;   // (T)
+    const double *sc;     // (T) per-step model constants or NULL
+    double *summaries;    // (T, 4)
+    const double *z_in, *u_in;
+    FilterDev *st;
+    double *partials;
+    unsigned int *ticket;
+    ScanState scan, scan2;
+    int64_t n, n_global, index_offset, T;
+    double essrmin;
+    Philox key;
+};
+
+__device__ __forceinline__ StepK step_consts(const FilterArgs &a, long long t) {
+    StepK k;
+    k.t = t;
+    k.y = a.data[t];
+    k.y_next = (t + 1 < a.T) ? a.data[t + 1] : 0.0;
+    k.sc0 = a.sc ? a.sc[t] : 0.0;
+    return k;
+}
+
+// compute_summaries (core.py:351-367) + time_to_resample for the next step (core.py:181-183)
+// executed by the whole last block; thread 0 owns the scalar work.
+template <bool APF>
+__device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w, const Lse3 &aux) {
+    __shared__ int s_next_flag;
+    if (threadIdx.x == 0) {
+        FilterDev *st = a.st;
+        const long long t = st->t;
+        const double N = (double)a.n_global;
+        double log_mean, ess;
+        weights_scalars(w, N, log_mean, ess);
+        const bool fresh = (t == 0) || (st->rs_flag != 0);
+        const double loglt = fresh ? log_mean : (log_mean - st->log_mean_w);   // core.py:355-358
+        const double logLt = st->logLt + loglt;
+        double *row = a.summaries + (size_t)t * SMCB_SUMMARY_STRIDE;
+        row[0] = ess; row[1] = logLt; row[2] = (double)st->rs_flag; row[3] = log_mean;
+        st->logLt = logLt; st->log_mean_w = log_mean; st->ess = ess;
+        st->wm = w.m; st->ws = w.s; st->wq = w.q;
+        st->last_rs = st->rs_flag;
+        const Lse3 &x = APF ? aux : w;
+        st->am = x.m; st->as = x.s; st->aq = x.q;
+        double lm_aux, ess_aux;
+        weights_scalars(x, N, lm_aux, ess_aux);
+        if (APF) st->reset_c = log(x.s) + x.m - log(w.s) - w.m;   // core.py:302 in closed form
+        int flag = (t + 1 < a.T) && (ess_aux < N * a.essrmin);    // strict <, NaN -> False
+        st->rs_flag = flag;
+        st->cur ^= 1;
+        st->t = t + 1;
+        s_next_flag = flag;
+    }
+    __syncthreads();
+    if (s_next_flag) {   // arm the look-back state of the next step's scans (saves a memset launch)
+        const int64_t tiles = (a.n + kScanTile - 1) / kScanTile;
+        const int64_t words = 2 + tiles + tiles / kScanGroup + 2;
+        unsigned long long *p = reinterpret_cast<unsigned long long *>(a.scan.ticket);
+        for (int64_t i = threadIdx.x; i < words; i += blockDim.x) p[i] = kNotReady;
+        if (a.su) {
+            const int64_t tiles2 = (a.n + 1 + kScanTile - 1) / kScanTile;
+            const int64_t words2 = 2 + tiles2 + tiles2 / kScanGroup + 2;
+            unsigned long long *q = reinterpret_cast<unsigned long long *>(a.scan2.ticket);
+            for (int64_t i = threadIdx.x; i < words2; i += blockDim.x) q[i] = kNotReady;
+        }
+    }
+}
+
+__device__ __forceinline__ double fix_nan(double v) { return v != v ? -CUDART_INF : v; }  // resampling.py:220
+
+// ---------------------------------------------------------------------------
+// t = 0: generate_particles + reweight (core.py:315-324, 373-374)
+// ---------------------------------------------------------------------------
+template <class M, int FK>
+__global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
+    constexpr bool APF = FkTraits<FK>::apf;
+    __shared__ Lse3 smem[kBlock / 32];
+    const StepK k = step_consts(a, 0);
+    double *Xo = a.X[0], *lwo = a.lw[0];
+    Lse3 acc[APF ? 2 : 1];
+    acc[0] = lse3_empty();
+    if (APF) acc[APF ? 1 : 0] = lse3_empty();
+    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x; p < npairs; p += stride) {
+        double z[2], x[2], l[2];
+        if (a.z_in) {
+            z[0] = a.z_in[2 * p];
+            z[1] = (2 * p + 1 < n) ? a.z_in[2 * p + 1] : 0.0;
+        } else {
+            normal_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, 0u, z[0], z[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double d;
+            fk_init<M, FK>(model, k, z[j], x[j], d);
+            l[j] = fix_nan(d);
+        }
+        if (2 * p + 1 < n) {
+            st2(Xo + 2 * p, x[0], x[1]);
+            st2(lwo + 2 * p, l[0], l[1]);
+        } else {
+            Xo[2 * p] = x[0];
+            lwo[2 * p] = l[0];
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (2 * p + j < n) {
+                lse3_add(acc[0], l[j]);
+                if (APF && a.T > 1) lse3_add(acc[APF ? 1 : 0], fix_nan(l[j] + model.logeta(k, x[j])));
+            }
+        }
+    }
+    Lse3 tot[APF ? 2 : 1];
+    if (!grid_merge_lse3<kBlock, (APF ? 2 : 1)>(acc, a.partials, a.ticket, smem, tot)) return;
+    if (threadIdx.x == 0) a.st->cur = 1;   // finalize flips it to 0: step 0 wrote buffers [0]
+    finalize_step<APF>(a, tot[0], tot[APF ? 1 : 0]);
+}
+
+// ---------------------------------------------------------------------------
+// resampling steps: normalised (auxiliary) weights -> CDF   (resampling.py:223-225 + scan)
+// ---------------------------------------------------------------------------
+template <class M, int FK>
+struct LoadWeights {
+    const double *lw, *X;
+    double m, s;
+    M model;
+    StepK kprev;   // step t-1 with y_next = data[t]: what logeta(t-1, X) needs
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+        constexpr bool APF = FkTraits<FK>::apf;
+        double l[8], x[8];
+        if (i0 + 8 <= n) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { double2 t = ld2(lw + i0 + j); l[j] = t.x; l[j + 1] = t.y; }
+            if (APF) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) { double2 t = ld2(X + i0 + j); x[j] = t.x; x[j + 1] = t.y; }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                l[j] = (i0 + j < n) ? lw[i0 + j] : -CUDART_INF;
+                if (APF) x[j] = (i0 + j < n) ? X[i0 + j] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double e = l[j];
+            if (APF) e = fix_nan(e + model.logeta(kprev, x[j]));
+            v[j] = (i0 + j < n) ? exp(e - m) / s : 0.0;
+        }
+    }
+};
+
+template <class M, int FK>
+__global__ void __launch_bounds__(kBlock) k_scan_w(M model, FilterArgs a) {
+    const FilterDev *st = a.st;
+    if (!st->rs_flag) return;
+    const long long t = st->t;
+    LoadWeights<M, FK> load;
+    load.lw = a.lw[st->cur];
+    load.X = a.X[st->cur];
+    load.m = st->am;
+    load.s = st->as;
+    load.model = model;
+    load.kprev = step_consts(a, t - 1);
+    scan_tiles_loop<double, LoadWeights<M, FK>>(load, a.n, a.cdf, a.scan);
+}
+
+// multinomial: exponential spacings z = cumsum(-log u), M + 1 of them (resampling.py:536)
+struct LoadSpacings {
+    Philox key; uint32_t t; const double *u_in;
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            double u0, u1;
+            if (u_in) {
+                u0 = (i0 + j < n) ? u_in[i0 + j] : 1.0;
+                u1 = (i0 + j + 1 < n) ? u_in[i0 + j + 1] : 1.0;
+            } else {
+                uniform_pair(key, (uint64_t)((i0 + j) >> 1), t, kPurposeUniform, u0, u1);
+            }
+            v[j] = (i0 + j < n) ? -log(u0) : 0.0;
+            v[j + 1] = (i0 + j + 1 < n) ? -log(u1) : 0.0;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
+    const FilterDev *st = a.st;
+    if (!st->rs_flag) return;
+    LoadSpacings load{a.key, (uint32_t)st->t,
+                      a.u_in ? a.u_in + (size_t)st->t * (a.n + 1) : nullptr};
+    scan_tiles_loop<double, LoadSpacings>(load, a.n + 1, a.su, a.scan2);
+}
+
+// ---------------------------------------------------------------------------
+// the step kernel: resample_move + reweight_particles + compute_summaries
+// (core.py:323-367)
+// ---------------------------------------------------------------------------
+template <class M, int FK, int SCHEME>
+__global__ void __launch_bounds__(kBlock) k_move(M model, FilterArgs a) {
+    constexpr bool APF = FkTraits<FK>::apf;
+    constexpr int K = APF ? 2 : 1;
+    __shared__ Lse3 smem[kBlock / 32];
+    __shared__ double s_su[2];
+    const FilterDev *st = a.st;
+    const long long t = st->t;
+    const int cur = st->cur;
+    const bool rs = st->rs_flag != 0;
+    const double reset_c = st->reset_c;
+    const StepK k = step_consts(a, t);
+    const StepK kprev = step_consts(a, t - 1);
+    const double *__restrict__ Xi = a.X[cur];
+    const double *__restrict__ lwi = a.lw[cur];
+    double *__restrict__ Xo = a.X[cur ^ 1];
+    double *__restrict__ lwo = a.lw[cur ^ 1];
+    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const double *zin = a.z_in ? a.z_in + (size_t)t * n : nullptr;
+    const bool last_apf = APF && (t + 1 < a.T);
+
+    Lse3 acc[K];
+    acc[0] = lse3_empty();
+    if (APF) acc[K - 1] = lse3_empty();
+
+    auto finish_pair = [&](int64_t p, const double (&xp)[2], const double (&base)[2]) {
+        double z[2], x[2], l[2];
+        if (zin) {
+            z[0] = zin[2 * p];
+            z[1] = (2 * p + 1 < n) ? zin[2 * p + 1] : 0.0;
+        } else {
+            normal_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, 0u, z[0], z[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double d;
+            fk_move<M, FK>(model, k, xp[j], z[j], x[j], d);
+            l[j] = fix_nan(base[j] + d);                          // Weights.add, resampling.py:241-244
+        }
+        if (2 * p + 1 < n) {
+            st2(Xo + 2 * p, x[0], x[1]);
+            st2(lwo + 2 * p, l[0], l[1]);
+        } else {
+            Xo[2 * p] = x[0];
+            lwo[2 * p] = l[0];
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            if (2 * p + j < n) {
+                lse3_add(acc[0], l[j]);
+                if (last_apf) lse3_add(acc[K - 1], fix_nan(l[j] + model.logeta(k, x[j])));
+            }
+        }
+    };
+
+    if (!rs) {
+        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass
+        const int64_t stride = (int64_t)gridDim.x * kBlock;
+        for (int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x; p < npairs; p += stride) {
+            double xp[2], base[2];
+            if (2 * p + 1 < n) {
+                double2 tx = ld2(Xi + 2 * p), tl = ld2(lwi + 2 * p);
+                xp[0] = tx.x; xp[1] = tx.y; base[0] = tl.x; base[1] = tl.y;
+            } else {
+                xp[0] = Xi[2 * p]; xp[1] = 0.0; base[0] = lwi[2 * p]; base[1] = 0.0;
+            }
+            finish_pair(p, xp, base);
+        }
+    } else {
+        // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
+        const double M_ = (double)n;
+        const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
+        double u_sys = 0.0;
+        if (SCHEME == SMCB_RS_SYSTEMATIC) {
+            if (uin) u_sys = uin[0];
+            else { double u1; uniform_pair(a.key, 0ull, (uint32_t)t, kPurposeUniform, u_sys, u1); }
+        }
+        const double zlast = (SCHEME == SMCB_RS_MULTINOMIAL) ? a.su[n] : 1.0;
+        const int64_t ntiles = (npairs + kBlock - 1) / kBlock;
+        const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+        const int64_t tile_lo = (int64_t)blockIdx.x * per;
+        const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
+        int64_t lo = -1;
+        for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
+            const int64_t p = tile * kBlock + threadIdx.x;
+            const int64_t k0 = 2 * tile * kBlock;
+            const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+            double su[2] = {2.0, 2.0};
+            if (p < npairs) {
+                if (SCHEME == SMCB_RS_SYSTEMATIC) {                    // resampling.py:609
+                    su[0] = (u_sys + (double)(2 * p)) / M_;
+                    su[1] = (u_sys + (double)(2 * p + 1)) / M_;
+                } else if (SCHEME == SMCB_RS_STRATIFIED) {             // resampling.py:602
+                    double u0, u1;
+                    if (uin) { u0 = uin[2 * p]; u1 = (2 * p + 1 < n) ? uin[2 * p + 1] : 0.0; }
+                    else uniform_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t,
+                                      kPurposeUniform, u0, u1);
+                    su[0] = (u0 + (double)(2 * p)) / M_;
+                    su[1] = (u1 + (double)(2 * p + 1)) / M_;
+                } else {                                               // resampling.py:537
+                    su[0] = a.su[2 * p] / zlast;
+                    su[1] = (2 * p + 1 < n) ? a.su[2 * p + 1] / zlast : 2.0;
+                }
+                if (2 * p == k0) s_su[0] = su[0];
+                if (2 * p == k1) s_su[1] = su[0];
+                if (2 * p + 1 == k1) s_su[1] = su[1];
+            }
+            __syncthreads();
+            const double su_first = s_su[0], su_last = s_su[1];
+            if (lo < 0) lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
+            const int64_t hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);
+            const int64_t hi1 = hi < n ? hi + 1 : n;
+            if (p < npairs) {
+                int64_t a0 = lower_bound(a.cdf, lo, hi1, su[0]);
+                int64_t a1 = lower_bound(a.cdf, a0, hi1, su[1]);
+                a0 = a0 < n - 1 ? a0 : n - 1;
+                a1 = a1 < n - 1 ? a1 : n - 1;
+                double xp[2], base[2];
+                xp[0] = __ldg(Xi + a0);
+                xp[1] = __ldg(Xi + a1);
+                if (APF) {   // core.py:302: lw = log_mean_exp(logetat, W) - logetat[A]
+                    base[0] = reset_c - model.logeta(kprev, xp[0]);
+                    base[1] = reset_c - model.logeta(kprev, xp[1]);
+                } else {     // Weights() then add(delta): lw = delta
+                    base[0] = 0.0; base[1] = 0.0;
+                }
+                if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(a0, a1);
+                else a.A[2 * p] = a0;
+                finish_pair(p, xp, base);
+            }
+            lo = hi;
+            __syncthreads();
+        }
+    }
+
+    Lse3 tot[K];
+    if (!grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot)) return;
+    finalize_step<APF>(a, tot[0], tot[K - 1]);
+}
+
+}  // namespace smcb
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct smcb_filter {
+    smcb_ctx *ctx;
+    smcb_filter_desc desc;
+    FilterArgs args;
+    FilterDev *st;
+    double *sc_dev;
+    void *scan_mem;
+    int grid_move, grid_scan, grid_scan2;
+    int64_t t_host;       // host mirror of FilterDev.t (one launch sequence per step)
+    cudaEvent_t *timed_ev; // non-NULL inside smcb_filter_step_timed: event pairs per launch
+    int *timed_kind;
+    int (*launch_init)(smcb_filter *);
+    int (*launch_step)(smcb_filter *);
+};
+
+template <class M, int FK, int SCHEME>
+static int launch_step_t(smcb_filter *f) {
+    M model;
+    model.load(f->desc.params);
+    cudaStream_t s = f->ctx->stream;
+    cudaEvent_t *ev = f->timed_ev;
+    int j = 0;
+    auto before = [&]() { if (ev) cudaEventRecord(ev[2 * j], s); };
+    auto after = [&](int kind) { if (ev) { cudaEventRecord(ev[2 * j + 1], s); f->timed_kind[j] = kind; j++; } };
+    before();
+    k_scan_w<M, FK><<<f->grid_scan, kBlock, 0, s>>>(model, f->args);
+    after(1);
+    f->ctx->launches++;
+    if (SCHEME == SMCB_RS_MULTINOMIAL) {
+        before();
+        k_scan_spacings<<<f->grid_scan2, kBlock, 0, s>>>(f->args);
+        after(2);
+        f->ctx->launches++;
+    }
+    before();
+    k_move<M, FK, SCHEME><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
+    after(3);
+    f->ctx->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
+template <class M, int FK>
+static int launch_init_t(smcb_filter *f) {
+    M model;
+    model.load(f->desc.params);
+    k_init<M, FK><<<f->grid_move, kBlock, 0, f->ctx->stream>>>(model, f->args);
+    f->ctx->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
+template <class M, int FK>
+static int bind_scheme(smcb_filter *f) {
+    f->launch_init = launch_init_t<M, FK>;
+    switch (f->desc.scheme) {
+        case SMCB_RS_SYSTEMATIC: f->launch_step = launch_step_t<M, FK, SMCB_RS_SYSTEMATIC>; return SMCB_OK;
+        case SMCB_RS_STRATIFIED: f->launch_step = launch_step_t<M, FK, SMCB_RS_STRATIFIED>; return SMCB_OK;
+        case SMCB_RS_MULTINOMIAL: f->launch_step = launch_step_t<M, FK, SMCB_RS_MULTINOMIAL>; return SMCB_OK;
+        default:
+            set_error("fused filter: resampling scheme %d is not fused (use systematic, stratified or "
+                      "multinomial, or the unfused path)", f->desc.scheme);
+            return SMCB_ENOSYS;
+    }
+}
+
+template <class M>
+static int bind_fk(smcb_filter *f) {
+    switch (f->desc.fk) {
+        case SMCB_FK_BOOTSTRAP: return bind_scheme<M, SMCB_FK_BOOTSTRAP>(f);
+        case SMCB_FK_GUIDED:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_GUIDED>(f);
+        case SMCB_FK_APF:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_APF>(f);
+        case SMCB_FK_AUXBOOT:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_AUXBOOT>(f);
+        default:
+            set_error("fused filter: unknown Feynman-Kac kind %d", f->desc.fk);
+            return SMCB_EINVAL;
+    }
+    // the reference raises NotImplementedError from StateSpaceModel.proposal / logeta
+    set_error("fused filter: model %d implements no proposal/logeta (Feynman-Kac kind %d)",
+              f->desc.model, f->desc.fk);
+    return SMCB_ENOSYS;
+}
+
+extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_filter **out) {
+    SMCB_REQUIRE(c && d && out, "smcb_filter_create: NULL argument");
+    SMCB_REQUIRE(d->n >= 1 && d->T >= 1, "smcb_filter_create: need n >= 1 and T >= 1");
+    SMCB_REQUIRE(d->X[0] && d->X[1] && d->lw[0] && d->lw[1] && d->A && d->cdf && d->data && d->summaries,
+                 "smcb_filter_create: NULL device buffer");
+    SMCB_REQUIRE((d->index_offset & 1) == 0, "smcb_filter_create: index_offset must be even");
+    SMCB_REQUIRE(d->dim == 1, "smcb_filter_create: this build fuses 1-D states only (dim=%d)", d->dim);
+    SMCB_REQUIRE(d->essrmin >= 0.0 && d->essrmin <= 1.0, "smcb_filter_create: ESSrmin must be in [0, 1]");
+    smcb_filter *f = new (std::nothrow) smcb_filter();
+    SMCB_REQUIRE(f != nullptr, "smcb_filter_create: out of host memory");
+    f->ctx = c;
+    f->desc = *d;
+    f->t_host = 0;
+    f->timed_ev = nullptr;
+    f->timed_kind = nullptr;
+    int rc;
+    switch (d->model) {
+        case SMCB_MODEL_STOCHVOL: rc = bind_fk<StochVolM>(f); break;
+        case SMCB_MODEL_LINGAUSS: rc = bind_fk<LinGaussM>(f); break;
+        case SMCB_MODEL_GORDON: rc = bind_fk<GordonM>(f); break;
+        case SMCB_MODEL_THETALOGISTIC: rc = bind_fk<ThetaLogisticM>(f); break;
+        default:
+            set_error("fused filter: model id %d is not available in the fused 1-D family", d->model);
+            rc = SMCB_ENOSYS;
+    }
+    if (rc) { delete f; return rc; }
+
+    const int64_t n = d->n;
+    const size_t sb1 = (scan_state_bytes(n) + 63) & ~(size_t)63;
+    const size_t sb2 = (scan_state_bytes(n + 1) + 63) & ~(size_t)63;
+    const size_t part = (size_t)kMaxGrid * 8 * sizeof(double);
+    char *mem;
+    SMCB_CUDA(cudaMalloc(&mem, 256 + part + sb1 + sb2 + 64));
+    SMCB_CUDA(cudaMemsetAsync(mem, 0, 256 + part, c->stream));
+    SMCB_CUDA(cudaMemsetAsync(mem + 256 + part, 0xFF, sb1 + sb2, c->stream));
+    f->scan_mem = mem;
+    f->st = reinterpret_cast<FilterDev *>(mem);
+    FilterArgs &a = f->args;
+    memset(&a, 0, sizeof(a));
+    a.X[0] = d->X[0]; a.X[1] = d->X[1]; a.lw[0] = d->lw[0]; a.lw[1] = d->lw[1];
+    a.A = reinterpret_cast<long long *>(d->A);
+    a.cdf = d->cdf;
+    a.su = (d->scheme == SMCB_RS_MULTINOMIAL) ? d->scratch : nullptr;
+    SMCB_REQUIRE(d->scheme != SMCB_RS_MULTINOMIAL || d->scratch != nullptr,
+                 "smcb_filter_create: multinomial needs desc.scratch of n + 2 doubles");
+    a.data = d->data;
+    a.sc = d->step_consts;
+    a.summaries = d->summaries;
+    a.z_in = d->z_in; a.u_in = d->u_in;
+    a.st = f->st;
+    a.partials = reinterpret_cast<double *>(mem + 256);
+    a.ticket = reinterpret_cast<unsigned int *>(mem + 128);
+    char *sp = mem + 256 + part;
+    a.scan.ticket = reinterpret_cast<unsigned int *>(sp);
+    a.scan.agg = reinterpret_cast<unsigned long long *>(sp + 16);
+    a.scan.cpref = a.scan.agg + scan_tiles(n);
+    sp += sb1;
+    a.scan2.ticket = reinterpret_cast<unsigned int *>(sp);
+    a.scan2.agg = reinterpret_cast<unsigned long long *>(sp + 16);
+    a.scan2.cpref = a.scan2.agg + scan_tiles(n + 1);
+    a.n = n; a.n_global = d->n_global > 0 ? d->n_global : n;
+    a.index_offset = d->index_offset; a.T = d->T;
+    a.essrmin = d->essrmin;
+    a.key = key_of(d->seed);
+    f->grid_move = grid_for((n + 1) / 2, kBlock);
+    {
+        int64_t t1 = scan_tiles(n), t2 = scan_tiles(n + 1);
+        f->grid_scan = (int)(t1 < kMaxGrid ? t1 : kMaxGrid);
+        f->grid_scan2 = (int)(t2 < kMaxGrid ? t2 : kMaxGrid);
+    }
+    *out = f;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_filter_destroy(smcb_filter *f) {
+    if (!f) return SMCB_OK;
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->scan_mem);
+    delete f;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_filter_step(smcb_filter *f, int64_t nsteps) {
+    SMCB_REQUIRE(f != nullptr, "smcb_filter_step: NULL filter");
+    // host mirror of t: the device advances by exactly one per launched step
+    for (int64_t i = 0; i < nsteps; i++) {
+        if (f->t_host >= f->desc.T) {
+            set_error("smcb_filter_step: all %lld steps already done (StopIteration)", (long long)f->desc.T);
+            return SMCB_EINVAL;
+        }
+        int rc = (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
+        if (rc) return rc;
+        f->t_host++;
+    }
+    return SMCB_OK;
+}
+
+// Same as smcb_filter_step, with a CUDA-event pair around every kernel launch (on the
+// launching stream).  out[0..3] = summed device milliseconds of {init, scan, spacings, move},
+// out[4..7] = number of launches of each.  Synchronises once, at the end.
+extern "C" int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *out8) {
+    SMCB_REQUIRE(f && out8, "smcb_filter_step_timed: NULL argument");
+    SMCB_REQUIRE(nsteps >= 0 && nsteps <= 100000, "smcb_filter_step_timed: nsteps out of range");
+    SMCB_REQUIRE(f->t_host + nsteps <= f->desc.T, "smcb_filter_step_timed: past the last step");
+    cudaStream_t s = f->ctx->stream;
+    const bool multi = f->desc.scheme == SMCB_RS_MULTINOMIAL;
+    const int per = multi ? 3 : 2;
+    const size_t nev = (size_t)nsteps * per * 2 + 2;
+    cudaEvent_t *ev = new (std::nothrow) cudaEvent_t[nev];
+    SMCB_REQUIRE(ev != nullptr, "smcb_filter_step_timed: out of host memory");
+    for (size_t i = 0; i < nev; i++) SMCB_CUDA(cudaEventCreate(&ev[i]));
+    int *kind = new int[nev / 2];
+    size_t k = 0;
+    // re-implements launch_step with events in between: the kernels are the same objects
+    for (int64_t i = 0; i < nsteps; i++) {
+        if (f->t_host == 0) {
+            SMCB_CUDA(cudaEventRecord(ev[2 * k], s));
+            int rc = f->launch_init(f);
+            if (rc) return rc;
+            SMCB_CUDA(cudaEventRecord(ev[2 * k + 1], s));
+            kind[k++] = 0;
+        } else {
+            f->timed_ev = ev + 2 * k;
+            f->timed_kind = kind + k;
+            int rc = f->launch_step(f);
+            f->timed_ev = nullptr;
+            if (rc) return rc;
+            k += per;
+        }
+        f->t_host++;
+    }
+    SMCB_CUDA(cudaStreamSynchronize(s));
+    for (int j = 0; j < 8; j++) out8[j] = 0.0;
+    for (size_t i = 0; i < k; i++) {
+        float ms = 0.f;
+        SMCB_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+        out8[kind[i]] += ms;
+        out8[4 + kind[i]] += 1.0;
+    }
+    for (size_t i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    delete[] ev;
+    delete[] kind;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_filter_state(smcb_filter *f, double *out8) {
+    SMCB_REQUIRE(f && out8, "smcb_filter_state: NULL argument");
+    FilterDev h;
+    SMCB_CUDA(cudaMemcpyAsync(&h, f->st, sizeof(h), cudaMemcpyDeviceToHost, f->ctx->stream));
+    SMCB_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    out8[0] = (double)h.t; out8[1] = (double)h.cur; out8[2] = (double)h.last_rs; out8[3] = h.logLt;
+    out8[4] = h.ess; out8[5] = h.log_mean_w; out8[6] = h.wm; out8[7] = h.ws;
+    return SMCB_OK;
+}

@@ -1,0 +1,203 @@
+"""Probability distributions on the device -- the ``ProbDist`` subset that sits on the
+SMC hot path, same constructor arguments and
+``rvs`` / ``logpdf`` semantics as ``particles/distributions.py``.
+
+Parameters may be Python scalars or CUDA fp64 tensors of shape (N,) (resp. (N, d) /
+(d,) for MvNormal); array-valued parameters make the object a Markov kernel, exactly
+as in the reference (distributions.py:135-154).  Randomness comes from the context's
+Philox stream (``particles_b200.seed``); ``rvs(size, z=...)`` accepts injected
+standard normals for deterministic parity tests.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import as_device, context, empty, ptr
+
+HALFLOG2PI = 0.5 * np.log(2.0 * np.pi)
+
+
+def _split(v):
+    """scalar-or-array argument -> (device tensor or None, scalar)"""
+    if isinstance(v, torch.Tensor):
+        return (as_device(v) if v.ndim > 0 else None), (float(v) if v.ndim == 0 else 0.0)
+    if isinstance(v, np.ndarray) and v.ndim > 0 and v.size > 1:
+        return as_device(v), 0.0
+    return None, float(np.asarray(v).reshape(-1)[0])
+
+
+class ProbDist:
+    """particles/distributions.py:215-251."""
+    dim = 1
+    dtype = float
+
+    def shape(self, size):
+        if size is None:
+            return None
+        return (size,) if self.dim == 1 else (size, self.dim)
+
+    def logpdf(self, x):
+        raise NotImplementedError
+
+    def rvs(self, size=None):
+        raise NotImplementedError
+
+    def ppf(self, u):
+        raise NotImplementedError   # SQMC only: out of scope
+
+
+class LocScaleDist(ProbDist):
+    """particles/distributions.py:259-264."""
+
+    def __init__(self, loc=0.0, scale=1.0):
+        self.loc = loc
+        self.scale = scale
+
+
+class Normal(LocScaleDist):
+    """N(loc, scale^2) -- particles/distributions.py:267-285."""
+
+    def _n(self, size, *arrs):
+        for a in arrs:
+            if a is not None:
+                return a.shape[0]
+        return 1 if size is None else int(size)
+
+    def rvs(self, size=None, z=None):
+        la, l0 = _split(self.loc)
+        sa, s0 = _split(self.scale)
+        zd = None if z is None else as_device(z)
+        n = self._n(size, la, sa, zd)
+        ctx = context()
+        out = empty(n)
+        _lib.check(ctx.lib.smcb_normal_rvs(ctx.handle, ptr(la), l0, ptr(sa), s0, ptr(zd), ptr(out), n))
+        return out
+
+    def logpdf(self, x):
+        xa, x0 = _split(x)
+        la, l0 = _split(self.loc)
+        sa, s0 = _split(self.scale)
+        n = self._n(None, xa, la, sa)
+        ctx = context()
+        out = empty(n)
+        _lib.check(ctx.lib.smcb_normal_logpdf(ctx.handle, ptr(xa), x0, ptr(la), l0, ptr(sa), s0,
+                                              ptr(out), n))
+        return out
+
+
+class Dirac(ProbDist):
+    """Dirac mass -- particles/distributions.py:454-472."""
+
+    def __init__(self, loc=0.0):
+        self.loc = loc
+
+    def rvs(self, size=None, z=None):
+        if isinstance(self.loc, torch.Tensor) and self.loc.ndim > 0:
+            return self.loc.clone()
+        n = 1 if size is None else size
+        return torch.full((n,), float(self.loc), dtype=torch.float64, device="cuda")
+
+    def logpdf(self, x):
+        x = as_device(x)
+        loc = self.loc if isinstance(self.loc, torch.Tensor) else float(self.loc)
+        zero = torch.zeros((), dtype=torch.float64, device=x.device)
+        return torch.where(x == loc, zero, zero - float("inf"))
+
+
+class IndepProd(ProbDist):
+    """Product of independent univariate laws -- particles/distributions.py:1066-1109.
+    Inputs / outputs are (N, d) tensors."""
+
+    def __init__(self, *dists):
+        self.dists = dists
+        self.dim = len(dists)
+
+    def logpdf(self, x):
+        x = as_device(x)
+        out = None
+        for i, d in enumerate(self.dists):
+            li = d.logpdf(x[..., i].contiguous())
+            out = li if out is None else out + li
+        return out
+
+    def rvs(self, size=None, z=None):
+        cols, k = [], 0
+        for d in self.dists:
+            if isinstance(d, Dirac) or z is None:
+                cols.append(d.rvs(size=size))
+            else:
+                cols.append(d.rvs(size=size, z=as_device(z)[:, k].contiguous()))
+                k += 1
+        return torch.stack(cols, dim=1)
+
+
+class MvNormal(ProbDist):
+    """Multivariate Normal -- particles/distributions.py:888-982 (d <= 8 on the device).
+    ``loc``: (d,) or (N, d); ``scale``: scalar, (d,) or (N, d); ``cov``: (d, d) host array."""
+
+    def __init__(self, loc=0.0, scale=1.0, cov=None):
+        self.loc = loc
+        self.scale = scale
+        if cov is None:
+            cov = np.eye(loc.shape[-1])
+        self.cov = np.asarray(cov.cpu() if isinstance(cov, torch.Tensor) else cov, dtype=np.float64)
+        err_msg = "MvNormal: argument cov must be a (d, d) pos. definite matrix"
+        try:
+            self.L = np.linalg.cholesky(self.cov)     # distributions.py:937
+        except np.linalg.LinAlgError:
+            raise ValueError(err_msg)
+        assert self.cov.shape == (self.dim, self.dim), err_msg
+
+    @property
+    def dim(self):
+        return self.cov.shape[-1]
+
+    def _params(self, v, default):
+        """-> (SoA device array (d, n) or None, host vector (d,))"""
+        d = self.dim
+        if isinstance(v, torch.Tensor):
+            if v.ndim == 2:
+                return v.t().contiguous(), None
+            v = v.cpu().numpy()
+        a = np.asarray(v, dtype=np.float64)
+        if a.ndim == 2:
+            return as_device(a).t().contiguous(), None
+        return None, np.ascontiguousarray(np.broadcast_to(a, (d,)), dtype=np.float64)
+
+    @staticmethod
+    def _hp(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def rvs(self, size=None, z=None):
+        d = self.dim
+        la, l0 = self._params(self.loc, 0.0)
+        sa, s0 = self._params(self.scale, 1.0)
+        zd = None if z is None else as_device(z).t().contiguous()
+        n = la.shape[1] if la is not None else (sa.shape[1] if sa is not None else
+                                                (zd.shape[1] if zd is not None else
+                                                 (1 if size is None else int(size))))
+        ctx = context()
+        out = empty((d, n))
+        L = np.ascontiguousarray(self.L)
+        _lib.check(ctx.lib.smcb_mvnormal_rvs(ctx.handle, ptr(la), self._hp(l0), ptr(sa), self._hp(s0),
+                                             self._hp(L), d, ptr(zd), ptr(out), n))
+        return out.t().contiguous()
+
+    def logpdf(self, x):
+        d = self.dim
+        x = as_device(x)
+        xs = x.reshape(-1, d).t().contiguous()
+        la, l0 = self._params(self.loc, 0.0)
+        sa, s0 = self._params(self.scale, 1.0)
+        n = max(xs.shape[1], la.shape[1] if la is not None else 1,
+                sa.shape[1] if sa is not None else 1)
+        if xs.shape[1] == 1 and n > 1:             # one observation against N kernels
+            xs = xs.expand(d, n).contiguous()
+        ctx = context()
+        out = empty(n)
+        L = np.ascontiguousarray(self.L)
+        _lib.check(ctx.lib.smcb_mvnormal_logpdf(ctx.handle, ptr(xs), ptr(la), self._hp(l0), ptr(sa),
+                                                self._hp(s0), self._hp(L), d, ptr(out), n))
+        return out

@@ -1,0 +1,297 @@
+"""GPU parity tests of the SMC step loop (fused kernels and plugin path) against the
+oracle, the reference's golden runs and the exact Kalman answers.
+
+* injected noise: the oracle and the device consume the SAME normals / uniforms, so
+  every per-step quantity can be compared directly (ancestors bit-exact, fp64 to the
+  tolerances written below);
+* device Philox: logLt is compared with the reference's own Monte-Carlo spread
+  (tests/golden/golden_stats.npz), the "3 sigma" bar of the north-star.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import smc_numpy as orc  # noqa: E402
+import philox_ref  # noqa: E402
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def lst(y):
+    return [np.atleast_1d(v) for v in y]
+
+
+def make_noise(N, T, scheme, seed):
+    r = np.random.RandomState(seed)
+    z = r.standard_normal((T, N))
+    u = r.rand(T, N + 1)
+    return z, u
+
+
+def oracle_noise(z, u, scheme, N):
+    nu = {"systematic": 1, "stratified": N, "multinomial": N + 1}[scheme]
+    return orc.InjectedNoise(z, [row[:nu] for row in u])
+
+
+def models():
+    from particles_b200 import kalman, state_space_models as ssm
+    return {
+        "sv": (ssm.StochVol(), orc.StochVol(), "data/sv_seed1_T1000", 60),
+        "lg": (kalman.LinearGauss(sigmaX=1.0, sigmaY=0.2, rho=0.9),
+               orc.LinearGauss(sigmaX=1.0, sigmaY=0.2, rho=0.9), "data/lg_seed2_T100", 100),
+        "gordon": (ssm.Gordon_etal(), orc.Gordon_etal(), "data/gordon_seed3_T50", 50),
+        "thetalog": (ssm.ThetaLogistic(), orc.ThetaLogistic(), "data/thetalogistic_seed4_T50", 50),
+    }
+
+
+FK = {"boot": ("Bootstrap", "Bootstrap"), "guided": ("GuidedPF", "GuidedPF"),
+      "apf": ("AuxiliaryPF", "AuxiliaryPF"), "auxboot": ("AuxiliaryBootstrap", "AuxiliaryBootstrap")}
+
+CASES = [
+    ("sv", "boot", "systematic", 0.5), ("sv", "boot", "stratified", 0.5),
+    ("sv", "boot", "multinomial", 0.5), ("sv", "boot", "systematic", 1.0),
+    ("sv", "guided", "systematic", 0.5), ("sv", "apf", "multinomial", 0.5),
+    ("sv", "apf", "systematic", 0.7), ("sv", "auxboot", "stratified", 0.5),
+    ("lg", "boot", "stratified", 0.5), ("lg", "guided", "stratified", 0.5),
+    ("lg", "apf", "systematic", 0.5), ("gordon", "boot", "systematic", 0.5),
+    ("thetalog", "boot", "stratified", 0.5),
+]
+
+
+@pytest.mark.parametrize("mname,fkname,scheme,essrmin", CASES)
+@pytest.mark.parametrize("N", [2000, 2049])
+def test_fused_step_by_step_vs_oracle(golden, mname, fkname, scheme, essrmin, N):
+    """Same noise in, same filter out: rs_flags and ancestors exact, X / lw / ESS / logLt
+    to fp64 round-off (1e-11: a few ulp per transcendental, accumulated over T steps)."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    dev_m, orc_m, dkey, T = models()[mname]
+    y = lst(golden[dkey][:T])
+    z, u = make_noise(N, T, scheme, 7)
+    fk_d = getattr(ssm, FK[fkname][0])(ssm=dev_m, data=y)
+    fk_o = getattr(orc, FK[fkname][1])(orc_m, y)
+    pf = pb.SMC(fk=fk_d, N=N, resampling=scheme, ESSrmin=essrmin, noise=(z, u), fused=True)
+    ref = orc.SMC(fk_o, N=N, resampling=scheme, ESSrmin=essrmin, noise=oracle_noise(z, u, scheme, N),
+                  keep=True)
+    assert pf.fused
+    n_rs = 0
+    for t in range(T):
+        next(pf)
+        ref.step()
+        assert pf.t == ref.t == t + 1
+        assert pf.rs_flag == ref.rs_flag, f"rs_flag differs at t={t}"
+        if ref.rs_flag:
+            n_rs += 1
+            A = host(pf.A)
+            assert A.dtype == np.int64
+            if scheme == "multinomial":
+                bad = np.flatnonzero(A != ref.A)        # second scan rounding: rare +-1 at CDF ties
+                assert bad.size <= 2 and np.all(np.abs(A[bad] - ref.A[bad]) <= 1)
+                if bad.size:
+                    pytest.skip("ancestor tie moved by scan rounding; trajectories diverge by design")
+            else:
+                assert np.array_equal(A, ref.A), f"ancestors differ at t={t}"
+        np.testing.assert_allclose(host(pf.X), ref.X, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(host(pf.wgts.lw), ref.wgts.lw, rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-10)
+        np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(pf.loglt, ref.loglt, rtol=1e-9, atol=1e-10)
+    assert n_rs > 0
+    np.testing.assert_allclose(host(pf.W), ref.wgts.W, rtol=1e-9, atol=1e-300)
+    assert np.array_equal(pf.summaries.rs_flags, ref.rs_flags)
+    np.testing.assert_allclose(pf.summaries.ESSs, ref.ESSs, rtol=1e-10)
+    np.testing.assert_allclose(pf.summaries.logLts, ref.logLts, rtol=1e-11, atol=1e-10)
+
+
+def test_sv_bootstrap_particles_bitexact(golden):
+    """StochVol bootstrap: x' = c + rho*xp + sigma*z is pure IEEE arithmetic, so with the
+    same normals and the same ancestors the particle arrays must be BIT-identical."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    N, T = 4096, 40
+    y = lst(golden["data/sv_seed1_T1000"][:T])
+    z, u = make_noise(N, T, "systematic", 3)
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, noise=(z, u))
+    ref = orc.SMC(orc.Bootstrap(orc.StochVol(), y), N=N, noise=oracle_noise(z, u, "systematic", N))
+    for t in range(T):
+        next(pf)
+        ref.step()
+        assert np.array_equal(host(pf.X), ref.X), f"t={t}"
+
+
+def test_run_equals_stepping_and_device_rng_layout(golden):
+    """run() (no host sync) == step-by-step, and the device Philox stream is the documented
+    one: replaying the host restatement of it as injected noise reproduces the run."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    N, T, seed = 3000, 50, 2024
+    y = lst(golden["data/sv_seed1_T1000"][:T])
+    mk = lambda **kw: pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N,  # noqa: E731
+                             resampling="stratified", seed=seed, **kw)
+    a = mk()
+    a.run()
+    b = mk()
+    for _ in b:
+        pass
+    assert a.logLt == b.logLt and np.array_equal(host(a.X), host(b.X))
+    assert a.summaries.ESSs == b.summaries.ESSs and a.summaries.rs_flags == b.summaries.rs_flags
+    assert len(a.summaries.logLts) == T and a.cpu_time > 0
+    z = np.stack([philox_ref.normals(N, t, seed) for t in range(T)])
+    u = np.stack([np.concatenate([philox_ref.uniforms(N, t, seed), [0.0]]) for t in range(T)])
+    c = mk(noise=(z, u))
+    c.run()
+    assert c.summaries.rs_flags == a.summaries.rs_flags
+    np.testing.assert_allclose(c.logLt, a.logLt, rtol=1e-12)
+    np.testing.assert_allclose(host(c.X), host(a.X), rtol=1e-10, atol=1e-12)
+    d = mk()
+    d._engine.close()
+    e = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, resampling="stratified", seed=seed + 1)
+    e.run()
+    assert e.logLt != a.logLt
+
+
+def test_plugin_path_matches_fused(golden):
+    """A user-defined model (README ToySSM, written against particles_b200.distributions)
+    runs through the plugin API; the same model expressed as LinearGauss runs fused."""
+    import particles_b200 as pb
+    from particles_b200 import distributions as dists, kalman, state_space_models as ssm
+
+    class ToySSM(ssm.StateSpaceModel):
+        default_params = {"sigma": 0.2}
+
+        def PX0(self):
+            return dists.Normal()
+
+        def PX(self, t, xp):
+            return dists.Normal(loc=xp)
+
+        def PY(self, t, xp, x):
+            return dists.Normal(loc=x, scale=self.sigma)
+
+    y = lst(golden["data/toy_seed0_T200"])
+    N = 1000
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=ToySSM(), data=y), N=N, seed=5)
+    assert not pf.fused
+    pf.run()
+    assert len(pf.summaries.ESSs) == 200 and pf.t == 200
+    fz = pb.SMC(fk=ssm.Bootstrap(ssm=kalman.LinearGauss(rho=1.0, sigmaX=1.0, sigmaY=0.2, sigma0=1.0),
+                                 data=y), N=N, seed=6)
+    assert fz.fused
+    fz.run()
+    ref = float(golden["run/toy_c1/logLt"][0])      # one reference run at N=1000; sd(logLt) ~ 1.2
+    assert abs(pf.logLt - ref) < 8 and abs(fz.logLt - ref) < 8
+    assert sum(pf.summaries.rs_flags) > 150 and sum(fz.summaries.rs_flags) > 150
+
+
+def test_plugin_path_step_parity_vs_oracle(golden):
+    """Plugin path with injected normals through a user FeynmanKac: same decisions as the oracle."""
+    import particles_b200 as pb
+    from particles_b200 import distributions as dists
+    N, T = 1500, 30
+    y = golden["data/lg_seed2_T100"][:T]
+    r = np.random.RandomState(1)
+    z = r.standard_normal((T, N))
+
+    class FK(pb.FeynmanKac):
+        def M0(self, N):
+            return dists.Normal(scale=2.0).rvs(size=N, z=z[0])
+
+        def M(self, t, xp):
+            return dists.Normal(loc=0.9 * xp, scale=1.0).rvs(size=xp.shape[0], z=z[t])
+
+        def logG(self, t, xp, x):
+            return dists.Normal(loc=x, scale=0.2).logpdf(y[t])
+
+    pf = pb.SMC(fk=FK(T), N=N, resampling="systematic", seed=1)
+    assert not pf.fused
+    om = orc.LinearGauss(sigmaX=1.0, sigmaY=0.2, rho=0.9, sigma0=2.0)
+    ref = orc.SMC(orc.Bootstrap(om, lst(y)), N=N, resampling="systematic",
+                  noise=orc.InjectedNoise(z, [None] * T))
+    # the resampling uniform of the plugin path comes from the device stream, so compare the
+    # weight / ESS / logLt recursions up to the first resampling step
+    for t in range(T):
+        next(pf)
+        if t > 0 and pf.rs_flag:
+            break
+        ref.step()
+        np.testing.assert_allclose(host(pf.X), ref.X, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-11)
+        np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-12)
+    assert t >= 1
+    pf.run()
+    assert pf.t == T and len(pf.summaries.logLts) == T
+
+
+@pytest.mark.parametrize("fkname,N", [("boot", 100_000), ("guided", 10_000), ("apf", 10_000)])
+def test_lingauss_exact_kalman(golden, golden_stats, fkname, N):
+    """Known answer: Kalman log-likelihood (kalman.py:459-517).  The estimator is unbiased for
+    the likelihood; its logLt spread is taken from the reference's own runs at N=1e4."""
+    import particles_b200 as pb
+    from particles_b200 import kalman, state_space_models as ssm
+    y = lst(golden["data/lg_seed2_T100"])
+    exact = float(np.sum(golden["kalman/lg_logpyt"]))
+    ref = golden_stats[f"stat/lg_T100_N10000_{fkname}/logLt"]
+    sd = ref.std(ddof=1) * np.sqrt(10000 / N)
+    lg = kalman.LinearGauss(sigmaX=1.0, sigmaY=0.2, rho=0.9)
+    runs = []
+    for s in range(8):
+        pf = pb.SMC(fk=getattr(ssm, FK[fkname][0])(ssm=lg, data=y), N=N, resampling="stratified",
+                    seed=100 + s)
+        pf.run()
+        runs.append(pf.logLt)
+    runs = np.array(runs)
+    # mean of 8 runs within 4 sd/sqrt(8) (+ the O(sd^2/2) Jensen bias of log) of the exact value
+    assert abs(runs.mean() - exact) < 4 * sd / np.sqrt(8) + sd ** 2, (runs, exact, sd)
+    assert 0.3 * sd < runs.std(ddof=1) < 3 * sd
+
+
+def test_sv_config2_statistics(golden, golden_stats):
+    """C2-shaped run (T=1000, systematic, ESSrmin=.5) at N=1e5 with the device generator:
+    logLt within 3 sigma of the reference's mean, sigma from the reference's own 8 runs;
+    resampling count in the reference's range."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    y = lst(golden_stats["data/sv_seed1_T1000"])
+    ref = golden_stats["stat/sv_T1000_N100000/logLt"]
+    nrs = golden_stats["stat/sv_T1000_N100000/n_resample"]
+    mu, sd = ref.mean(), ref.std(ddof=1)
+    out = []
+    for s in range(4):
+        pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=100_000, seed=s)
+        pf.run()
+        out.append(pf.logLt)
+        assert nrs.min() - 3 <= sum(pf.summaries.rs_flags) <= nrs.max() + 3
+        assert abs(pf.logLt - mu) < 3 * sd * np.sqrt(1 + 1 / len(ref)) + 1e-9, (pf.logLt, mu, sd)
+    assert abs(np.mean(out) - mu) / abs(mu) < 1e-4        # relative error of logLt
+
+
+def test_full_size_properties_1e7(golden_stats):
+    """BASELINE config 2 at full N=1e7 (T truncated to 60 steps): size-independent properties."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    N, T = 10_000_000, 60
+    y = lst(golden_stats["data/sv_seed1_T1000"][:T])
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, ESSrmin=1.0, seed=9)
+    for t in range(T):
+        next(pf)
+        if t in (1, 30, T - 1):
+            assert pf.rs_flag                                # ESSrmin = 1: every step resamples
+            A = host(pf.A)
+            cdf = host(pf._engine.cdf)
+            assert np.all(np.diff(cdf) >= 0) and abs(cdf[-1] - 1) < 1e-12
+            u = philox_ref.uniforms(2, t, 9)[0]
+            su = (u + np.arange(N)) / N
+            assert np.array_equal(A, np.minimum(np.searchsorted(cdf, su, "left"), N - 1))
+            assert np.all(np.diff(A) >= 0)
+    # likelihood of the first 60 observations: compare with an oracle run at N=2e5 (sd ~ 0.01)
+    ref = orc.SMC(orc.Bootstrap(orc.StochVol(), y), N=200_000)
+    np.random.seed(0)
+    ref.run()
+    assert abs(pf.logLt - ref.logLt) < 0.08
+    w = pf.wgts
+    assert 1 <= w.ESS <= N and abs(float(w.W.sum().item()) - 1) < 1e-10

@@ -1,0 +1,294 @@
+"""GPU parity tests for the L0 numerics (weights algebra, scan, search, resampling,
+distributions) -- all calls go through the C-ABI of libsmcb.so (via the ctypes host
+layer).  Checker = the oracle + golden vectors produced by the live reference.
+
+Bars: bit-exact for ancestor indices and anything integer; for fp64 the tolerances
+are written next to each assert (transcendentals differ from NumPy's by <= a few ulp).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cext  # noqa: E402
+from oracle import smc_numpy as orc  # noqa: E402
+import philox_ref  # noqa: E402
+
+LW_CASES = ["gauss_1000", "equal_257", "dominant_513", "neginf_777", "nan_300", "single_1",
+            "wide_4099", "tiny_2"]
+RS_CASES = ["dirichlet_1000", "skewed_513", "M_lt_N", "M_gt_N", "zeros_300", "dominant_64",
+            "equal_1025", "n7"]
+SCHEMES = ["systematic", "stratified", "multinomial", "residual"]
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import particles_b200 as pb
+    return pb
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# --------------------------------------------------------------------------- RNG
+def test_philox_matches_host_reference(pb):
+    """The device generator is Philox4x32-10 with the documented counter layout
+    (known-answer vectors are checked on the CPU side in test_host.py)."""
+    from particles_b200 import _lib
+    from particles_b200.device import context, empty, ptr
+    ctx = context()
+    ctx.seed(0x1234567890ABCDEF)
+    u = empty(1001)
+    _lib.check(ctx.lib.smcb_uniform(ctx.handle, ptr(u), 1001))
+    ref = philox_ref.uniforms(1001, 0, 0x1234567890ABCDEF, w3=philox_ref.PURPOSE_API)
+    assert np.array_equal(host(u), ref)           # integer pipeline + exact scaling: bit-exact
+    z = empty(1001)
+    _lib.check(ctx.lib.smcb_standard_normal(ctx.handle, ptr(z), 1001))
+    refz = philox_ref.normals(1001, 1, 0x1234567890ABCDEF, w3=philox_ref.PURPOSE_API)
+    np.testing.assert_allclose(host(z), refz, rtol=1e-13, atol=1e-15)   # log/sincos: few ulp
+    big = empty(2_000_000)
+    _lib.check(ctx.lib.smcb_standard_normal(ctx.handle, ptr(big), big.shape[0]))
+    b = host(big)
+    assert abs(b.mean()) < 5 / np.sqrt(b.size) and abs(b.var() - 1) < 5 * np.sqrt(2 / b.size)
+    assert abs((b ** 4).mean() - 3) < 0.05
+
+
+# ----------------------------------------------------------------------- weights
+@pytest.mark.parametrize("name", LW_CASES)
+def test_weights_vs_reference(pb, golden, name):
+    from particles_b200 import resampling as rs
+    lw_in = golden[f"w/{name}/lw_in"]
+    lw = dev(lw_in.copy())
+    w = rs.Weights(lw=lw)
+    ref_stats, ref_W = golden[f"w/{name}/stats"], golden[f"w/{name}/W"]
+    assert not np.isnan(host(lw)).any()           # NaN -> -inf in the caller's array (resampling.py:220)
+    assert host(w.lw).max() == ref_stats[0]       # max is exact
+    # log_mean / ESS: summation order + exp differ -> 1e-13 relative
+    np.testing.assert_allclose([w.log_mean, w.ESS], ref_stats[1:], rtol=1e-13)
+    np.testing.assert_allclose(host(w.W), ref_W, rtol=1e-13, atol=1e-300)
+    fin = lw_in.copy()
+    fin[np.isnan(fin)] = -np.inf
+    lse = golden[f"w/{name}/lse"]
+    np.testing.assert_allclose([rs.log_sum_exp(dev(fin)), rs.log_mean_exp(dev(fin)), rs.essl(dev(fin))],
+                               lse, rtol=1e-13)
+    np.testing.assert_allclose(host(rs.exp_and_normalise(dev(fin))),
+                               golden[f"w/{name}/exp_and_normalise"], rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(rs.log_mean_exp(dev(fin), W=dev(golden[f"w/{name}/Wn"])),
+                               golden[f"w/{name}/log_mean_exp_W"][0], rtol=1e-13)
+
+
+def test_weights_edge_semantics(pb):
+    from particles_b200 import resampling as rs
+    w = rs.Weights()
+    assert w.N == 0 and not hasattr(w, "W") and not hasattr(w, "ESS") and not hasattr(w, "log_mean")
+    w2 = w.add(dev(np.array([0.0, -1.0, -2.0])))
+    assert w2.N == 3 and w.lw is None             # add returns a NEW object
+    ref = orc.Weights(lw=np.array([0.0, -1.0, -2.0]))
+    np.testing.assert_allclose([w2.ESS, w2.log_mean], [ref.ESS, ref.log_mean], rtol=1e-14)
+    w3 = w2.add(dev(np.array([1.0, 1.0, 5.0])))
+    ref3 = ref.add(np.array([1.0, 1.0, 5.0]))
+    np.testing.assert_allclose(host(w3.W), ref3.W, rtol=1e-14)
+    # all -inf and +inf inputs: NaN W / ESS / log_mean, no exception
+    for bad in (np.full(5, -np.inf), np.array([0.0, np.inf, 1.0])):
+        wb = rs.Weights(lw=dev(bad.copy()))
+        assert np.isnan(wb.ESS) and np.isnan(wb.log_mean)
+    # exactly equal weights, ESSrmin = 1.0 -> ESS == N up to rounding, strict < is the caller's test
+    we = rs.Weights(lw=dev(np.zeros(4096)))
+    assert we.ESS == 4096.0 and we.log_mean == 0.0
+
+
+def test_weights_large_matches_oracle(pb):
+    from particles_b200 import resampling as rs
+    r = np.random.RandomState(3)
+    lw = r.randn(3_000_001) * 4.0
+    ref = orc.Weights(lw=lw.copy())
+    w = rs.Weights(lw=dev(lw))
+    np.testing.assert_allclose([w.log_mean, w.ESS], [ref.log_mean, ref.ESS], rtol=1e-12)
+    np.testing.assert_allclose(host(w.W), ref.W, rtol=1e-12, atol=1e-300)
+    mv = rs.wmean_and_var(w.W, dev(lw))
+    refmv = orc.wmean_and_var(ref.W, lw)
+    np.testing.assert_allclose([mv["mean"], mv["var"]], [refmv["mean"], refmv["var"]], rtol=1e-10)
+
+
+# -------------------------------------------------------------------------- scan
+@pytest.mark.parametrize("n", [1, 7, 2047, 2048, 2049, 65536 + 3, 1_000_003, 10_000_000])
+def test_cumsum_monotone_deterministic(pb, n):
+    from particles_b200 import resampling as rs
+    r = np.random.RandomState(n % 1000)
+    W = r.rand(n) ** 8
+    W[r.rand(n) < 0.3] = 0.0                       # many exact zeros (ties in the CDF)
+    W = W / W.sum()
+    Wd = dev(W)
+    c1, c2 = host(rs.cumsum(Wd)), host(rs.cumsum(Wd))
+    assert np.array_equal(c1, c2)                  # a pure function of the input
+    assert np.all(np.diff(c1) >= 0)                # non-decreasing by construction
+    ref = np.cumsum(W)
+    np.testing.assert_allclose(c1, ref, rtol=1e-13, atol=1e-15)
+    assert abs(c1[-1] - 1.0) < 1e-13
+
+
+def test_cumsum_adversarial_tiny_weights(pb):
+    """Weights below 1 ulp of the running sum: the clamped scan must stay monotone."""
+    from particles_b200 import resampling as rs
+    n = 300_000
+    W = np.full(n, 1e-25)
+    W[::4099] = 1.0
+    W /= W.sum()
+    c = host(rs.cumsum(dev(W)))
+    assert np.all(np.diff(c) >= 0)
+    np.testing.assert_allclose(c, np.cumsum(W), rtol=1e-13, atol=1e-16)
+
+
+# ------------------------------------------------------------------------ search
+@pytest.mark.parametrize("name", RS_CASES)
+def test_inverse_cdf_vs_reference(pb, golden, name):
+    from particles_b200 import resampling as rs
+    W, su = golden[f"rs/{name}/W"], golden[f"rs/{name}/su"]
+    A = host(rs.inverse_cdf(dev(su), dev(W)))
+    assert A.dtype == np.int64
+    cdf = host(rs.cumsum(dev(W)))
+    assert np.array_equal(A, cext.searchsorted_left(cdf, su))       # bit-exact on the device's CDF
+    assert np.array_equal(A, golden[f"rs/{name}/inverse_cdf"])       # and equal to the reference here
+
+
+@pytest.mark.parametrize("name", RS_CASES)
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_resampling_vs_reference_injected_uniforms(pb, golden, name, scheme):
+    """Same W, same uniforms (in the reference's draw order) -> same ancestors."""
+    from particles_b200 import resampling as rs
+    W, M = golden[f"rs/{name}/W"], int(golden[f"rs/{name}/M"][0])
+    u = golden[f"rs/{name}/{scheme}/u"]
+    A = host(rs.rs_funcs[scheme](dev(W), M=M, u=u))
+    ref = golden[f"rs/{name}/{scheme}/A"]
+    assert A.shape == ref.shape and A.dtype == np.int64
+    if scheme in ("systematic", "stratified"):
+        assert np.array_equal(A, ref)
+    else:
+        # multinomial / residual go through a second scan (cumsum of -log u) whose rounding
+        # differs from np.cumsum: a draw that lands within 1e-15 of a CDF value may move by one
+        bad = np.flatnonzero(A != ref)
+        assert bad.size <= max(1, M // 500) and np.all(np.abs(A[bad] - ref[bad]) <= 1)
+
+
+def test_unknown_scheme_raises(pb, golden):
+    from particles_b200 import resampling as rs
+    with pytest.raises(ValueError) as e:
+        rs.resampling("bogus", dev(golden["rs/n7/W"]))
+    assert str(e.value) == bytes(golden["rs/bogus_error"]).decode()
+
+
+@pytest.mark.parametrize("scheme", ["systematic", "stratified", "multinomial"])
+@pytest.mark.parametrize("n,m", [(10_000_000, 10_000_000), (1_000_003, 777_777), (5000, 20_001)])
+def test_resampling_bitexact_on_own_cdf_large(pb, scheme, n, m):
+    """Full-size property test: ancestors == np.searchsorted(device CDF, device su)."""
+    from particles_b200 import resampling as rs
+    r = np.random.RandomState(11)
+    lw = r.randn(n) * 3.0
+    W = orc.exp_and_normalise(lw)
+    Wd = dev(W)
+    nu = {"systematic": 1, "stratified": m, "multinomial": m + 1}[scheme]
+    u = r.rand(nu)
+    A, scratch = rs._resample(scheme, Wd, m, u=u, return_scratch=True)
+    A = host(A)
+    cdf = host(scratch[:n])
+    assert np.array_equal(cdf, host(rs.cumsum(Wd)))
+    if scheme == "multinomial":
+        off = (n + 1) & ~1
+        z = host(scratch[off: off + m + 1])
+        su = z[:-1] / z[-1]
+        np.testing.assert_allclose(z, np.cumsum(-np.log(u)), rtol=1e-12)
+    else:
+        su = (u + np.arange(m)) / m               # the reference's expression, IEEE-exact on both sides
+    ref = np.minimum(np.searchsorted(cdf, su, side="left"), n - 1)
+    assert np.array_equal(A, ref)
+    assert np.all(np.diff(A) >= 0)                 # sorted output (resampling.py:548-552)
+    if scheme == "systematic" and m == n:
+        cnt = np.bincount(A, minlength=n)
+        assert np.all(np.abs(cnt - n * W) < 1.0 + 1e-6)      # offspring in {floor, ceil}(N W)
+        # vs the reference's sequential inverse_cdf on np.cumsum: only 1-ulp CDF ties may differ
+        mism = np.count_nonzero(A != orc.inverse_cdf(su, W))
+        assert mism <= n * 1e-6
+
+
+def test_residual_structure_large(pb):
+    from particles_b200 import resampling as rs
+    r = np.random.RandomState(5)
+    n = 200_003
+    W = orc.exp_and_normalise(r.randn(n) * 2.0)
+    u = r.rand(n + 1)
+    A = host(rs.residual(dev(W), u=u))
+    ip = np.floor(n * W).astype(np.int64)
+    sip = int(ip.sum())
+    assert np.array_equal(A[:sip], np.arange(n).repeat(ip))        # deterministic part: exact
+    ref = orc.residual(W, n, u=u)
+    bad = np.flatnonzero(A != ref)
+    assert bad.size <= n // 1000 and np.all(np.abs(A[bad] - ref[bad]) <= 1)
+    assert np.all(np.diff(A[sip:]) >= 0)
+
+
+def test_gather(pb):
+    from particles_b200 import _lib
+    from particles_b200.device import context, empty, ptr
+    ctx = context()
+    r = np.random.RandomState(0)
+    X = r.randn(3, 1001)
+    A = r.randint(0, 1001, size=777).astype(np.int64)
+    out = empty((3, 777))
+    _lib.check(ctx.lib.smcb_gather(ctx.handle, ptr(dev(X)), 1001, ptr(dev(A)), 777, 3, ptr(out)))
+    assert np.array_equal(host(out), X[:, A])
+    Xr = np.ascontiguousarray(X.T)
+    out2 = empty((777, 3))
+    _lib.check(ctx.lib.smcb_gather_rows(ctx.handle, ptr(dev(Xr)), 1001, ptr(dev(A)), 777, 3, ptr(out2)))
+    assert np.array_equal(host(out2), Xr[A])
+
+
+# ----------------------------------------------------------------- distributions
+def test_normal_vs_reference(pb, golden):
+    from particles_b200 import distributions as dists
+    g = golden
+    x, loc, scale = g["d/normal/x"], g["d/normal/loc"], g["d/normal/scale"]
+    lp = host(dists.Normal(loc=dev(loc), scale=dev(scale)).logpdf(dev(x)))
+    np.testing.assert_allclose(lp, g["d/normal/logpdf"], rtol=1e-14, atol=1e-15)   # 1 log + 1 div
+    lp2 = host(dists.Normal(loc=0.3, scale=1.7).logpdf(dev(x)))
+    np.testing.assert_allclose(lp2, g["d/normal/logpdf_scalar"], rtol=1e-14, atol=1e-15)
+    # rvs with the reference's own normals: loc + scale*z is pure IEEE arithmetic -> bit-exact
+    xs = host(dists.Normal(loc=dev(loc), scale=dev(scale)).rvs(size=500, z=g["d/normal/rvs_z"]))
+    assert np.array_equal(xs, g["d/normal/rvs"])
+
+
+def test_mvnormal_vs_reference(pb, golden):
+    from particles_b200 import distributions as dists
+    g = golden
+    cov, locs, xs, sc = g["d/mvn/cov"], g["d/mvn/loc"], g["d/mvn/x"], g["d/mvn/scale"]
+    lp = host(dists.MvNormal(loc=dev(locs), cov=cov).logpdf(dev(xs)))
+    np.testing.assert_allclose(lp, g["d/mvn/logpdf"], rtol=1e-13)
+    lp2 = host(dists.MvNormal(loc=dev(locs), scale=sc, cov=cov).logpdf(dev(xs)))
+    np.testing.assert_allclose(lp2, g["d/mvn/logpdf_scaled"], rtol=1e-13)
+    rv = host(dists.MvNormal(loc=dev(locs), scale=sc, cov=cov).rvs(size=200, z=g["d/mvn/rvs_z"]))
+    np.testing.assert_allclose(rv, g["d/mvn/rvs"], rtol=1e-14, atol=1e-15)   # dot-product order
+    with pytest.raises(ValueError):
+        dists.MvNormal(loc=np.zeros(2), cov=np.array([[1.0, 2.0], [2.0, 1.0]]))
+
+
+def test_indepprod_dirac_vs_reference(pb, golden):
+    from particles_b200 import state_space_models as ssm
+    g = golden
+    xp = dev(g["d/indep/xp"])
+    law = ssm.BearingsOnly().PX(1, xp)
+    xn = g["d/indep/rvs"]
+    # recover the two columns of normals the reference drew, then replay them
+    z = np.stack([(xn[:, 0] - g["d/indep/xp"][:, 0]) / 2e-4, (xn[:, 1] - g["d/indep/xp"][:, 1]) / 2e-4], 1)
+    out = host(law.rvs(size=50, z=z))
+    np.testing.assert_allclose(out, xn, rtol=1e-12, atol=1e-15)
+    assert np.array_equal(out[:, 2:], xn[:, 2:])                     # Dirac components: exact
+    np.testing.assert_allclose(host(law.logpdf(dev(xn))), g["d/indep/logpdf"], rtol=1e-13)
+    lpy = host(ssm.BearingsOnly().PY(1, xp, dev(xn)).logpdf(np.array([0.7])))
+    np.testing.assert_allclose(lpy, g["d/indep/bearing_logpdf"], rtol=1e-12)
