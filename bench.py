@@ -296,7 +296,7 @@ def run_b200(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"StochVol bootstrap filter, N={n} particles per GPU "
-                               f"(global {total_n}), T={K}, systematic resampling, ESSrmin=0.5 "
+                               f"(global {total_n}), T={K}, systematic resampling, ESSrmin={ESSRMIN} "
                                "(BASELINE config 2" + (")" if world == 1 else "/4, particle-sharded)"),
                    "l2": "working set 4 x 80 MB of fp64 state per GPU > 126 MB L2 (no flush needed)",
                    "resampling_steps": n_rs, "logLt": logLt,
@@ -317,7 +317,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--essrmin", type=float, default=0.5,
+                    help="0.5 = BASELINE config 2; 1.0 = resample at every step (stress case)")
     args = ap.parse_args()
+    global ESSRMIN
+    ESSRMIN = args.essrmin
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -123,6 +123,10 @@ int smcb_mvnormal_logpdf(smcb_ctx *ctx, const double *x, const double *loc,
 int smcb_standard_normal(smcb_ctx *ctx, double *out, int64_t n);
 int smcb_uniform(smcb_ctx *ctx, double *out, int64_t n);
 
+/* test hook: the step kernel's own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
+ * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1) */
+int smcb_device_math(smcb_ctx *ctx, int fn, const double *x, double *out, int64_t n);
+
 /* ---------------------------------------------------------------------------
  * fused filter: the whole step of core.py:369-383 for a recognised model
  * ------------------------------------------------------------------------- */

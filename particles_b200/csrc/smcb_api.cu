@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "smcb_common.cuh"
+#include "smcb_math.cuh"
 #include "smcb_reduce.cuh"
 #include "smcb_scan.cuh"
 #include "smcb_search.cuh"
@@ -787,5 +788,28 @@ extern "C" int smcb_mvnormal_logpdf(smcb_ctx *c, const double *x, const double *
     int rc = fill_mvn(&P, loc0, scale0, L, d);
     if (rc) return rc;
     LAUNCH(c, k_mvn_logpdf, grid_for(n, kBlock * 2), kBlock, P, x, loc, scale, out, n);
+    return SMCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// test hook: evaluate the step kernel's fp64 elementary functions (smcb_math.cuh) on an array
+// fn: 0 fexp, 1 flog_pos, 2 sin(2 pi u), 3 cos(2 pi u)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_device_math(int fn, const double *__restrict__ x,
+                                                       double *__restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        double r, s, c;
+        if (fn == 0) r = fexp(v);
+        else if (fn == 1) r = flog_pos(v);
+        else { fsincos2pi(v, s, c); r = (fn == 2) ? s : c; }
+        out[i] = r;
+    }
+}
+
+extern "C" int smcb_device_math(smcb_ctx *c, int fn, const double *x, double *out, int64_t n) {
+    SMCB_REQUIRE(c && x && out && n >= 1 && fn >= 0 && fn <= 3, "smcb_device_math: bad argument");
+    LAUNCH(c, k_device_math, grid_for(n, kBlock * 4), kBlock, fn, x, out, n);
     return SMCB_OK;
 }

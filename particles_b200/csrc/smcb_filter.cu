@@ -18,6 +18,7 @@
 #include <new>
 
 #include "smcb_common.cuh"
+#include "smcb_math.cuh"
 #include "smcb_models.cuh"
 #include "smcb_reduce.cuh"
 #include "smcb_scan.cuh"
@@ -120,27 +121,30 @@ __device__ __forceinline__ double fix_nan(double v) { return v != v ? -CUDART_IN
 template <class M, int FK>
 __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
+    constexpr int K = APF ? 2 : 1;
     __shared__ Lse3 smem[kBlock / 32];
     const StepK k = step_consts(a, 0);
     double *Xo = a.X[0], *lwo = a.lw[0];
-    Lse3 acc[APF ? 2 : 1];
+    Lse3 acc[K];
     acc[0] = lse3_empty();
-    if (APF) acc[APF ? 1 : 0] = lse3_empty();
+    if (APF) acc[K - 1] = lse3_empty();
     const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const bool has_next = APF && a.T > 1;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x; p < npairs; p += stride) {
-        double z[2], x[2], l[2];
+        double z[2], x[2], l[2], av[2];
         if (a.z_in) {
             z[0] = a.z_in[2 * p];
             z[1] = (2 * p + 1 < n) ? a.z_in[2 * p + 1] : 0.0;
         } else {
-            normal_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, 0u, z[0], z[1]);
+            normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, 0u, z[0], z[1]);
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             double d;
             fk_init<M, FK>(model, k, z[j], x[j], d);
             l[j] = fix_nan(d);
+            av[j] = has_next ? fix_nan(l[j] + model.logeta(k, x[j])) : -CUDART_INF;
         }
         if (2 * p + 1 < n) {
             st2(Xo + 2 * p, x[0], x[1]);
@@ -148,19 +152,15 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
         } else {
             Xo[2 * p] = x[0];
             lwo[2 * p] = l[0];
+            l[1] = -CUDART_INF; av[1] = -CUDART_INF;   // masked slot contributes exactly 0
         }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            if (2 * p + j < n) {
-                lse3_add(acc[0], l[j]);
-                if (APF && a.T > 1) lse3_add(acc[APF ? 1 : 0], fix_nan(l[j] + model.logeta(k, x[j])));
-            }
-        }
+        lse3_add_batch<2>(acc[0], l);
+        if (APF) lse3_add_batch<2>(acc[K - 1], av);
     }
-    Lse3 tot[APF ? 2 : 1];
-    if (!grid_merge_lse3<kBlock, (APF ? 2 : 1)>(acc, a.partials, a.ticket, smem, tot)) return;
+    Lse3 tot[K];
+    if (!grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot)) return;
     if (threadIdx.x == 0) a.st->cur = 1;   // finalize flips it to 0: step 0 wrote buffers [0]
-    finalize_step<APF>(a, tot[0], tot[APF ? 1 : 0]);
+    finalize_step<APF>(a, tot[0], tot[K - 1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -193,7 +193,7 @@ struct LoadWeights {
         for (int j = 0; j < 8; j++) {
             double e = l[j];
             if (APF) e = fix_nan(e + model.logeta(kprev, x[j]));
-            v[j] = (i0 + j < n) ? exp(e - m) / s : 0.0;
+            v[j] = (i0 + j < n) ? fexp(e - m) / s : 0.0;
         }
     }
 };
@@ -226,7 +226,7 @@ struct LoadSpacings {
             } else {
                 uniform_pair(key, (uint64_t)((i0 + j) >> 1), t, kPurposeUniform, u0, u1);
             }
-            v[j] = (i0 + j < n) ? -log(u0) : 0.0;
+            v[j] = (i0 + j < n) ? -log(u0) : 0.0;       // u may be 0 or injected: library log
             v[j + 1] = (i0 + j + 1 < n) ? -log(u1) : 0.0;
         }
     }
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 // (core.py:323-367)
 // ---------------------------------------------------------------------------
 template <class M, int FK, int SCHEME>
-__global__ void __launch_bounds__(kBlock) k_move(M model, FilterArgs a) {
+__global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
     constexpr int K = APF ? 2 : 1;
     __shared__ Lse3 smem[kBlock / 32];
@@ -269,19 +269,23 @@ __global__ void __launch_bounds__(kBlock) k_move(M model, FilterArgs a) {
     acc[0] = lse3_empty();
     if (APF) acc[K - 1] = lse3_empty();
 
-    auto finish_pair = [&](int64_t p, const double (&xp)[2], const double (&base)[2]) {
-        double z[2], x[2], l[2];
+    // propagate + reweight one pair of particles; writes x', lw'; returns lw' (and the
+    // auxiliary log-weights of the next step for an APF), -inf in masked slots
+    auto do_pair = [&](int64_t p, const double (&xp)[2], const double (&base)[2], double *l,
+                       double *av) {
+        double z[2], x[2];
         if (zin) {
             z[0] = zin[2 * p];
             z[1] = (2 * p + 1 < n) ? zin[2 * p + 1] : 0.0;
         } else {
-            normal_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, 0u, z[0], z[1]);
+            normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, 0u, z[0], z[1]);
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             double d;
             fk_move<M, FK>(model, k, xp[j], z[j], x[j], d);
             l[j] = fix_nan(base[j] + d);                          // Weights.add, resampling.py:241-244
+            if (APF) av[j] = last_apf ? fix_nan(l[j] + model.logeta(k, x[j])) : -CUDART_INF;
         }
         if (2 * p + 1 < n) {
             st2(Xo + 2 * p, x[0], x[1]);
@@ -289,28 +293,39 @@ __global__ void __launch_bounds__(kBlock) k_move(M model, FilterArgs a) {
         } else {
             Xo[2 * p] = x[0];
             lwo[2 * p] = l[0];
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            if (2 * p + j < n) {
-                lse3_add(acc[0], l[j]);
-                if (last_apf) lse3_add(acc[K - 1], fix_nan(l[j] + model.logeta(k, x[j])));
-            }
+            l[1] = -CUDART_INF;
+            if (APF) av[1] = -CUDART_INF;
         }
     };
 
     if (!rs) {
-        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass
+        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread
+        constexpr int kU = 4;
         const int64_t stride = (int64_t)gridDim.x * kBlock;
-        for (int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x; p < npairs; p += stride) {
-            double xp[2], base[2];
-            if (2 * p + 1 < n) {
-                double2 tx = ld2(Xi + 2 * p), tl = ld2(lwi + 2 * p);
-                xp[0] = tx.x; xp[1] = tx.y; base[0] = tl.x; base[1] = tl.y;
-            } else {
-                xp[0] = Xi[2 * p]; xp[1] = 0.0; base[0] = lwi[2 * p]; base[1] = 0.0;
+        for (int64_t p0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; p0 < npairs; p0 += kU * stride) {
+            double xp[kU][2], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {                        // all loads first (MLP)
+                const int64_t p = p0 + u * stride;
+                if (p < npairs && 2 * p + 1 < n) {
+                    double2 tx = ld2(Xi + 2 * p), tl = ld2(lwi + 2 * p);
+                    xp[u][0] = tx.x; xp[u][1] = tx.y; base[u][0] = tl.x; base[u][1] = tl.y;
+                } else if (p < npairs) {
+                    xp[u][0] = Xi[2 * p]; xp[u][1] = 0.0; base[u][0] = lwi[2 * p]; base[u][1] = 0.0;
+                }
             }
-            finish_pair(p, xp, base);
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int64_t p = p0 + u * stride;
+                if (p < npairs) {
+                    do_pair(p, xp[u], base[u], l + 2 * u, APF ? av + 2 * u : av);
+                } else {
+                    l[2 * u] = l[2 * u + 1] = -CUDART_INF;
+                    if (APF) av[APF ? 2 * u : 0] = av[APF ? 2 * u + 1 : 0] = -CUDART_INF;
+                }
+            }
+            lse3_add_batch<2 * kU>(acc[0], l);
+            if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(acc[K - 1], av);
         }
     } else {
         // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
@@ -372,7 +387,10 @@ __global__ void __launch_bounds__(kBlock) k_move(M model, FilterArgs a) {
                 }
                 if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(a0, a1);
                 else a.A[2 * p] = a0;
-                finish_pair(p, xp, base);
+                double l[2], av[2];
+                do_pair(p, xp, base, l, av);
+                lse3_add_batch<2>(acc[0], l);
+                if (APF) lse3_add_batch<2>(acc[K - 1], av);
             }
             lo = hi;
             __syncthreads();

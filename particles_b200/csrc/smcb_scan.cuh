@@ -117,22 +117,42 @@ __device__ __forceinline__ void scan_tiles_loop(const LOAD &load, int64_t n, T *
         // look-back: warp 0 rebuilds this tile's exclusive prefix P_t and P_{t+1}
         if (warp == 0) {
             const unsigned int g = tile / kScanGroup, rr = tile % kScanGroup;
-            unsigned int k = g;
+            // (1) nearest published group prefix C_k, k <= g: 32 candidates per probe round
+            //     (lane l looks at C_{base-l}); C_0 = 0 is published by definition.
+            unsigned int k = 0;
             T c = 0;
-            while (k > 0) {   // nearest published group prefix (lane 0 reads, warp agrees)
-                unsigned long long b = (lane == 0) ? ld_volatile_u64(st.cpref + k) : 0ull;
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (b != kNotReady) { c = from_bits<T>(b); break; }
-                k--;
+            for (int base = (int)g;; base -= 32) {
+                const int idx = base - lane;
+                unsigned long long b = kNotReady;
+                if (idx >= 1) b = ld_volatile_u64(st.cpref + idx);
+                else if (idx == 0) b = canon_bits((T)0);
+                const unsigned int ready = __ballot_sync(0xffffffffu, b != kNotReady);
+                if (ready) {
+                    const int first = __ffs(ready) - 1;          // smallest lane = largest index
+                    k = (unsigned int)(base - first);
+                    c = from_bits<T>(__shfl_sync(0xffffffffu, b, first));
+                    break;
+                }
             }
-            for (; k < g; k++) {   // fold whole groups k .. g-1 (all their tiles precede ours)
-                unsigned long long b;
-                do { b = ld_volatile_u64(st.agg + (size_t)k * kScanGroup + lane); } while (b == kNotReady);
-                T sg = warp_scan_monotone(from_bits<T>(b), lane);
-                sg = __shfl_sync(0xffffffffu, sg, 31);
-                c = c + sg;
-                if (lane == 0)
-                    *reinterpret_cast<volatile unsigned long long *>(st.cpref + k + 1) = canon_bits(c);
+            // (2) fold whole groups k .. g-1 (all their tiles precede ours): the loads of up to
+            //     4 groups are issued together, the fold itself is sequential in a fixed order.
+            for (; k < g; k += 4) {
+                unsigned long long b4[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    b4[i] = (k + i < g) ? ld_volatile_u64(st.agg + (size_t)(k + i) * kScanGroup + lane) : 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (k + i < g) {
+                        while (b4[i] == kNotReady)
+                            b4[i] = ld_volatile_u64(st.agg + (size_t)(k + i) * kScanGroup + lane);
+                        T sg = warp_scan_monotone(from_bits<T>(b4[i]), lane);
+                        sg = __shfl_sync(0xffffffffu, sg, 31);
+                        c = c + sg;
+                        if (lane == 0)
+                            *reinterpret_cast<volatile unsigned long long *>(st.cpref + k + i + 1) = canon_bits(c);
+                    }
+                }
             }
             T a = 0;
             if ((unsigned int)lane < rr) {

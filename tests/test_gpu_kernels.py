@@ -61,6 +61,38 @@ def test_philox_matches_host_reference(pb):
     assert abs((b ** 4).mean() - 3) < 0.05
 
 
+def test_device_math(pb):
+    """csrc/smcb_math.cuh (the step kernel's own exp / log / sincos) against NumPy: <= 2 ulp."""
+    from particles_b200 import _lib
+    from particles_b200.device import context, empty, ptr
+    ctx = context()
+    r = np.random.RandomState(0)
+
+    def run(fn, x):
+        xd, out = dev(x), empty(x.shape[0])
+        _lib.check(ctx.lib.smcb_device_math(ctx.handle, fn, ptr(xd), ptr(out), x.shape[0]))
+        return host(out)
+
+    x = np.concatenate([r.uniform(-745, 5, 200_000), r.uniform(-2, 2, 200_000),
+                        [0.0, -0.0, -708.0, -1e-300, 1e-17, 700.0, -np.inf, -800.0]])
+    e = run(0, x)
+    ref = np.exp(x)
+    ok = x >= -708
+    np.testing.assert_allclose(e[ok], ref[ok], rtol=4.5e-16)            # 2 ulp
+    assert np.all(e[~ok] == 0.0)                                        # flushed tail < 3e-308
+    assert np.isnan(run(0, np.array([np.nan, 1.0]))[0])
+    u = np.concatenate([r.rand(300_000), 1 - 2.0 ** -np.arange(1, 54), 2.0 ** -np.arange(1, 55),
+                        r.uniform(0, 1e6, 1000)])
+    u = u[u > 0]
+    np.testing.assert_allclose(run(1, u), np.log(u), rtol=4.5e-16, atol=2.3e-16)
+    v = np.concatenate([r.rand(300_000), np.arange(0, 1, 1 / 64), [0.0, 0.25, 0.5, 0.75, 1 - 2.0 ** -53]])
+    import mpmath
+    np.testing.assert_allclose(run(2, v), np.sin(2 * np.pi * v), atol=4.5e-16, rtol=0)
+    np.testing.assert_allclose(run(3, v), np.cos(2 * np.pi * v), atol=4.5e-16, rtol=0)
+    exact = [float(mpmath.sin(2 * mpmath.pi * mpmath.mpf(float(t)))) for t in v[:2000]]
+    np.testing.assert_allclose(run(2, v)[:2000], exact, rtol=4.5e-16, atol=1e-300)
+
+
 # ----------------------------------------------------------------------- weights
 @pytest.mark.parametrize("name", LW_CASES)
 def test_weights_vs_reference(pb, golden, name):
