@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libsmcb.so")
+SO_PATH = os.environ.get("SMCB_LIB") or os.path.join(HERE, "libsmcb.so")   # SMCB_LIB: kernel-variant experiments
 
 SMCB_MAX_PARAMS = 256
 SUMMARY_STRIDE = 4

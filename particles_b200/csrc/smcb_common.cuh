@@ -50,6 +50,7 @@ inline int grid_for(int64_t work_items, int items_per_block) {
 // ---------------------------------------------------------------------------
 struct Philox {
     uint32_t k0, k1;
+    uint32_t rk[20];   // the 10 round keys (k0 + r*W0, k1 + r*W1), bumped once on the host
 };
 
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
@@ -66,6 +67,22 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
         uint32_t n2 = hi0 ^ c3 ^ k1;
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// same permutation with the round keys taken from the (constant-bank) Philox struct: saves the
+// 18 uniform key bumps per call that the generic version spends
+__device__ __forceinline__ void philox4x32_10k(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const Philox &key, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ key.rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ key.rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -98,8 +115,7 @@ __device__ __forceinline__ void box_muller(const uint32_t r[4], double &z0, doub
 __device__ __forceinline__ void normal_pair(const Philox &key, uint64_t pair, uint32_t t,
                                             uint32_t comp, double &z0, double &z1) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), t, (comp << 8) | kPurposeNormal, key.k0,
-                  key.k1, r);
+    philox4x32_10k((uint32_t)pair, (uint32_t)(pair >> 32), t, (comp << 8) | kPurposeNormal, key, r);
     box_muller(r, z0, z1);
 }
 
@@ -107,7 +123,7 @@ __device__ __forceinline__ void normal_pair(const Philox &key, uint64_t pair, ui
 __device__ __forceinline__ void uniform_pair(const Philox &key, uint64_t pair, uint32_t t,
                                              uint32_t purpose, double &u0, double &u1) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), t, purpose, key.k0, key.k1, r);
+    philox4x32_10k((uint32_t)pair, (uint32_t)(pair >> 32), t, purpose, key, r);
     u0 = u53(r[0], r[1]);
     u1 = u53(r[2], r[3]);
 }
@@ -207,5 +223,14 @@ namespace smcb {
 // workspace layout (doubles): [0, kWsPartials) block partials | 16 scalars | scan tile state
 constexpr size_t kWsPartials = 65536;
 constexpr size_t kWsBytes = 8u << 20;  // 8 MiB: partials + up to ~1M scan tiles
-inline Philox key_of(uint64_t seed) { return Philox{(uint32_t)seed, (uint32_t)(seed >> 32)}; }
+inline Philox key_of(uint64_t seed) {
+    Philox k;
+    k.k0 = (uint32_t)seed;
+    k.k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) {
+        k.rk[2 * r] = k.k0 + (uint32_t)r * 0x9E3779B9u;
+        k.rk[2 * r + 1] = k.k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return k;
+}
 }  // namespace smcb

@@ -55,6 +55,8 @@ struct FilterArgs {
     unsigned int *ticket;
     ScanState scan, scan2;
     int64_t n, n_global, index_offset, T;
+    int64_t chunk;        // pairs of particles per block (blocked assignment, multiple of kBlock)
+    double *tile_pref;    // (grid + 1) exclusive prefixes of the blocks' normalised weight mass
     double essrmin;
     Philox key;
 };
@@ -99,14 +101,45 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
         s_next_flag = flag;
     }
     __syncthreads();
-    if (s_next_flag) {   // arm the look-back state of the next step's scans (saves a memset launch)
-        const int64_t tiles = (a.n + kScanTile - 1) / kScanTile;
-        const int64_t words = 2 + tiles + tiles / kScanGroup + 2;
-        unsigned long long *p = reinterpret_cast<unsigned long long *>(a.scan.ticket);
-        for (int64_t i = threadIdx.x; i < words; i += blockDim.x) p[i] = kNotReady;
-        if (a.su) {
+    if (s_next_flag) {
+        // The blocks own contiguous particle ranges, so their partial sums ARE the tile
+        // aggregates of the weight scan of the next step: turn them into exclusive prefixes
+        // P_0 = 0 <= P_1 <= ... <= P_G here (fixed order, monotone), and the scan kernel needs
+        // no look-back at all.
+        __shared__ double s_w[kBlock / 32];
+        const int G = (int)gridDim.x, K = APF ? 2 : 1, j = APF ? 1 : 0;
+        const double xm = a.st->am, xs = a.st->as;
+        const int per = (G + kBlock - 1) / kBlock;
+        const int b0 = threadIdx.x * per;
+        double loc[8], run = 0.0;
+        for (int i = 0; i < per && i < 8; i++) {
+            const int b = b0 + i;
+            double v = 0.0;
+            if (b < G) {
+                const volatile double *pp = a.partials + (size_t)b * 4 * K + 4 * j;
+                v = pp[1] * fexp(pp[0] - xm) / xs;
+            }
+            run = run + v;
+            loc[i] = run;
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const double iw = warp_scan_monotone(run, lane);
+        if (lane == 31) s_w[warp] = iw;
+        __syncthreads();
+        double woff = 0.0;
+        for (int w = 0; w < kBlock / 32; w++)
+            if (w < warp) woff = woff + s_w[w];
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double cap = woff + iw;
+        if (threadIdx.x == 0) a.tile_pref[0] = 0.0;
+        for (int i = 0; i < per && i < 8; i++) {
+            const int b = b0 + i;
+            if (b < G) a.tile_pref[b + 1] = fmin(excl + loc[i], cap);
+        }
+        if (a.su) {   // multinomial: arm the look-back state of the spacings scan
             const int64_t tiles2 = (a.n + 1 + kScanTile - 1) / kScanTile;
-            const int64_t words2 = 2 + tiles2 + tiles2 / kScanGroup + 2;
+            const int64_t words2 = 2 + tiles2 + tiles2 + 2;
             unsigned long long *q = reinterpret_cast<unsigned long long *>(a.scan2.ticket);
             for (int64_t i = threadIdx.x; i < words2; i += blockDim.x) q[i] = kNotReady;
         }
@@ -130,8 +163,9 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
     if (APF) acc[K - 1] = lse3_empty();
     const int64_t n = a.n, npairs = (n + 1) >> 1;
     const bool has_next = APF && a.T > 1;
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x; p < npairs; p += stride) {
+    const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
+    const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+    for (int64_t p = pstart + threadIdx.x; p < pend; p += kBlock) {
         double z[2], x[2], l[2], av[2];
         if (a.z_in) {
             z[0] = a.z_in[2 * p];
@@ -202,6 +236,7 @@ template <class M, int FK>
 __global__ void __launch_bounds__(kBlock) k_scan_w(M model, FilterArgs a) {
     const FilterDev *st = a.st;
     if (!st->rs_flag) return;
+    __shared__ double s_warp[kBlock / 32];
     const long long t = st->t;
     LoadWeights<M, FK> load;
     load.lw = a.lw[st->cur];
@@ -210,7 +245,51 @@ __global__ void __launch_bounds__(kBlock) k_scan_w(M model, FilterArgs a) {
     load.s = st->as;
     load.model = model;
     load.kprev = step_consts(a, t - 1);
-    scan_tiles_loop<double, LoadWeights<M, FK>>(load, a.n, a.cdf, a.scan);
+    // block b scans the particles it owns, [2 b chunk, 2 (b+1) chunk), from the exclusive
+    // prefix P_b that finalize_step derived from the previous kernel's partial sums; every value
+    // is clamped into [P_b, P_{b+1}], so the CDF is non-decreasing across blocks by construction
+    const int64_t n = a.n;
+    const int64_t e0 = 2 * (int64_t)blockIdx.x * a.chunk;
+    const int64_t e1 = e0 + 2 * a.chunk < n ? e0 + 2 * a.chunk : n;
+    const double p_b = a.tile_pref[blockIdx.x], p_next = a.tile_pref[blockIdx.x + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double carry = 0.0;
+    for (int64_t base0 = e0; base0 < e1; base0 += kScanTile) {
+        const int64_t i0 = base0 + (int64_t)tid * kScanItems;
+        double r[kScanItems];
+        load(i0, e1, r);
+#pragma unroll
+        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
+        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
+        if (lane == 31) s_warp[warp] = iw;
+        __syncthreads();
+        double woff = 0.0, total = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) {
+            if (w < warp) woff = woff + s_warp[w];
+            total = total + s_warp[w];
+        }
+        const double incl = woff + iw;
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double b_i = p_b + carry;                       // base of this sub-tile
+        const double carry_next = carry + total;
+        const double b_next = fmin(p_b + carry_next, p_next); // base of the next one
+        const double tb = b_i + excl;
+        const double cap = fmin(b_i + incl, b_next);
+        double o[kScanItems];
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) o[j] = fmin(tb + r[j], cap);
+        if (i0 + kScanItems <= e1) {
+            store_items(a.cdf, i0, o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++)
+                if (i0 + j < e1) a.cdf[i0 + j] = o[j];
+        }
+        carry = carry_next;
+        __syncthreads();
+    }
 }
 
 // multinomial: exponential spacings z = cumsum(-log u), M + 1 of them (resampling.py:536)
@@ -244,12 +323,21 @@ __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 // the step kernel: resample_move + reweight_particles + compute_summaries
 // (core.py:323-367)
 // ---------------------------------------------------------------------------
+#ifndef SMCB_KU
+#define SMCB_KU 2
+#endif
+#ifndef SMCB_MINB
+#define SMCB_MINB 3
+#endif
 template <class M, int FK, int SCHEME>
-__global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
+__global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
     constexpr int K = APF ? 2 : 1;
+    constexpr int kStage = 2048;                       // doubles of CDF staged per output tile
     __shared__ Lse3 smem[kBlock / 32];
     __shared__ double s_su[2];
+    __shared__ __align__(16) double s_cdf[kStage];
+    __shared__ long long s_hi;
     const FilterDev *st = a.st;
     const long long t = st->t;
     const int cur = st->cur;
@@ -300,24 +388,26 @@ __global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
 
     if (!rs) {
         // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread
-        constexpr int kU = 4;
-        const int64_t stride = (int64_t)gridDim.x * kBlock;
-        for (int64_t p0 = (int64_t)blockIdx.x * kBlock + threadIdx.x; p0 < npairs; p0 += kU * stride) {
+        constexpr int kU = SMCB_KU;
+        constexpr int64_t stride = kBlock;
+        const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
+        const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+        for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kU * stride) {
             double xp[kU][2], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1];
 #pragma unroll
             for (int u = 0; u < kU; u++) {                        // all loads first (MLP)
                 const int64_t p = p0 + u * stride;
-                if (p < npairs && 2 * p + 1 < n) {
+                if (p < pend && 2 * p + 1 < n) {
                     double2 tx = ld2(Xi + 2 * p), tl = ld2(lwi + 2 * p);
                     xp[u][0] = tx.x; xp[u][1] = tx.y; base[u][0] = tl.x; base[u][1] = tl.y;
-                } else if (p < npairs) {
+                } else if (p < pend) {
                     xp[u][0] = Xi[2 * p]; xp[u][1] = 0.0; base[u][0] = lwi[2 * p]; base[u][1] = 0.0;
                 }
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 const int64_t p = p0 + u * stride;
-                if (p < npairs) {
+                if (p < pend) {
                     do_pair(p, xp[u], base[u], l + 2 * u, APF ? av + 2 * u : av);
                 } else {
                     l[2 * u] = l[2 * u + 1] = -CUDART_INF;
@@ -338,7 +428,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
         }
         const double zlast = (SCHEME == SMCB_RS_MULTINOMIAL) ? a.su[n] : 1.0;
         const int64_t ntiles = (npairs + kBlock - 1) / kBlock;
-        const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+        const int64_t per = a.chunk / kBlock;                  // chunk is a multiple of kBlock
         const int64_t tile_lo = (int64_t)blockIdx.x * per;
         const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
         int64_t lo = -1;
@@ -369,11 +459,34 @@ __global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
             __syncthreads();
             const double su_first = s_su[0], su_last = s_su[1];
             if (lo < 0) lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
-            const int64_t hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);
-            const int64_t hi1 = hi < n ? hi + 1 : n;
+            // stage the slice of the CDF this tile's outputs fall into (16 KB, coalesced 16-byte
+            // loads) and search it in shared memory; su is sorted, so the slice starts at `lo`
+            const int64_t sbase = lo & ~(int64_t)1;
+            const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
+            for (int i = 2 * threadIdx.x; i < cnt; i += 2 * kBlock) {
+                if (i + 1 < cnt) *reinterpret_cast<double2 *>(&s_cdf[i]) = ld2(a.cdf + sbase + i);
+                else s_cdf[i] = a.cdf[sbase + i];
+            }
+            __syncthreads();
+            const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= su_last);
+            int64_t hi = lo;
+            if (!covered) hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);   // rare: sparse mass
             if (p < npairs) {
-                int64_t a0 = lower_bound(a.cdf, lo, hi1, su[0]);
-                int64_t a1 = lower_bound(a.cdf, a0, hi1, su[1]);
+                int64_t a0, a1;
+                if (covered) {
+                    int l0 = (int)(lo - sbase), h0 = cnt;
+                    while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < su[0]) l0 = mid + 1; else h0 = mid; }
+                    int l1 = l0, h1 = cnt;
+                    while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < su[1]) l1 = mid + 1; else h1 = mid; }
+                    a0 = sbase + l0;
+                    a1 = sbase + l1;
+                    if (2 * p == k1) s_hi = a0;
+                    if (2 * p + 1 == k1) s_hi = a1;
+                } else {
+                    const int64_t hi1 = hi < n ? hi + 1 : n;
+                    a0 = lower_bound(a.cdf, lo, hi1, su[0]);
+                    a1 = lower_bound(a.cdf, a0, hi1, su[1]);
+                }
                 a0 = a0 < n - 1 ? a0 : n - 1;
                 a1 = a1 < n - 1 ? a1 : n - 1;
                 double xp[2], base[2];
@@ -392,8 +505,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_move(M model, FilterArgs a) {
                 lse3_add_batch<2>(acc[0], l);
                 if (APF) lse3_add_batch<2>(acc[K - 1], av);
             }
-            lo = hi;
             __syncthreads();
+            lo = covered ? (s_hi < n ? s_hi : n - 1) : hi;
         }
     }
 
@@ -414,7 +527,8 @@ struct smcb_filter {
     FilterDev *st;
     double *sc_dev;
     void *scan_mem;
-    int grid_move, grid_scan, grid_scan2;
+    int grid_move, grid_scan2;
+    int blocks_per_sm;    // resident CTAs/SM of the step kernel (persistent grid = SMs x this)
     int64_t t_host;       // host mirror of FilterDev.t (one launch sequence per step)
     cudaEvent_t *timed_ev; // non-NULL inside smcb_filter_step_timed: event pairs per launch
     int *timed_kind;
@@ -432,7 +546,7 @@ static int launch_step_t(smcb_filter *f) {
     auto before = [&]() { if (ev) cudaEventRecord(ev[2 * j], s); };
     auto after = [&](int kind) { if (ev) { cudaEventRecord(ev[2 * j + 1], s); f->timed_kind[j] = kind; j++; } };
     before();
-    k_scan_w<M, FK><<<f->grid_scan, kBlock, 0, s>>>(model, f->args);
+    k_scan_w<M, FK><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
     after(1);
     f->ctx->launches++;
     if (SCHEME == SMCB_RS_MULTINOMIAL) {
@@ -459,13 +573,22 @@ static int launch_init_t(smcb_filter *f) {
     return SMCB_OK;
 }
 
+template <class M, int FK, int SCHEME>
+static int bind_one(smcb_filter *f) {
+    f->launch_init = launch_init_t<M, FK>;
+    f->launch_step = launch_step_t<M, FK, SCHEME>;
+    int nb = 0;
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_move<M, FK, SCHEME>, kBlock, 0));
+    f->blocks_per_sm = nb < 1 ? 1 : nb;
+    return SMCB_OK;
+}
+
 template <class M, int FK>
 static int bind_scheme(smcb_filter *f) {
-    f->launch_init = launch_init_t<M, FK>;
     switch (f->desc.scheme) {
-        case SMCB_RS_SYSTEMATIC: f->launch_step = launch_step_t<M, FK, SMCB_RS_SYSTEMATIC>; return SMCB_OK;
-        case SMCB_RS_STRATIFIED: f->launch_step = launch_step_t<M, FK, SMCB_RS_STRATIFIED>; return SMCB_OK;
-        case SMCB_RS_MULTINOMIAL: f->launch_step = launch_step_t<M, FK, SMCB_RS_MULTINOMIAL>; return SMCB_OK;
+        case SMCB_RS_SYSTEMATIC: return bind_one<M, FK, SMCB_RS_SYSTEMATIC>(f);
+        case SMCB_RS_STRATIFIED: return bind_one<M, FK, SMCB_RS_STRATIFIED>(f);
+        case SMCB_RS_MULTINOMIAL: return bind_one<M, FK, SMCB_RS_MULTINOMIAL>(f);
         default:
             set_error("fused filter: resampling scheme %d is not fused (use systematic, stratified or "
                       "multinomial, or the unfused path)", f->desc.scheme);
@@ -513,10 +636,17 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     f->timed_kind = nullptr;
     int rc;
     switch (d->model) {
+#ifdef SMCB_BENCH_ONLY   // experiment builds: only the config-2 instantiation (fast compile)
+        case SMCB_MODEL_STOCHVOL:
+            rc = (d->fk == SMCB_FK_BOOTSTRAP && d->scheme == SMCB_RS_SYSTEMATIC)
+                     ? bind_one<StochVolM, SMCB_FK_BOOTSTRAP, SMCB_RS_SYSTEMATIC>(f) : SMCB_ENOSYS;
+            break;
+#else
         case SMCB_MODEL_STOCHVOL: rc = bind_fk<StochVolM>(f); break;
         case SMCB_MODEL_LINGAUSS: rc = bind_fk<LinGaussM>(f); break;
         case SMCB_MODEL_GORDON: rc = bind_fk<GordonM>(f); break;
         case SMCB_MODEL_THETALOGISTIC: rc = bind_fk<ThetaLogisticM>(f); break;
+#endif
         default:
             set_error("fused filter: model id %d is not available in the fused 1-D family", d->model);
             rc = SMCB_ENOSYS;
@@ -528,7 +658,8 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     const size_t sb2 = (scan_state_bytes(n + 1) + 63) & ~(size_t)63;
     const size_t part = (size_t)kMaxGrid * 8 * sizeof(double);
     char *mem;
-    SMCB_CUDA(cudaMalloc(&mem, 256 + part + sb1 + sb2 + 64));
+    const size_t tpb = (size_t)(kMaxGrid + 8) * sizeof(double);
+    SMCB_CUDA(cudaMalloc(&mem, 256 + part + sb1 + sb2 + tpb + 64));
     SMCB_CUDA(cudaMemsetAsync(mem, 0, 256 + part, c->stream));
     SMCB_CUDA(cudaMemsetAsync(mem + 256 + part, 0xFF, sb1 + sb2, c->stream));
     f->scan_mem = mem;
@@ -560,10 +691,22 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     a.index_offset = d->index_offset; a.T = d->T;
     a.essrmin = d->essrmin;
     a.key = key_of(d->seed);
-    f->grid_move = grid_for((n + 1) / 2, kBlock);
+    a.tile_pref = reinterpret_cast<double *>(mem + 256 + part + sb1 + sb2);
+    {   // persistent grid: one wave of resident CTAs, each owning a contiguous range of pairs
+        int dev = 0, sms = kSMs;
+        SMCB_CUDA(cudaGetDevice(&dev));
+        SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int64_t npairs = (n + 1) / 2;
+        const int64_t unit = (int64_t)kBlock * SMCB_KU;            // pairs per block iteration
+        int64_t g = (int64_t)sms * f->blocks_per_sm;
+        if (g > kMaxGrid) g = kMaxGrid;
+        int64_t chunk = ((npairs + g - 1) / g + unit - 1) / unit * unit;
+        g = (npairs + chunk - 1) / chunk;
+        a.chunk = chunk;
+        f->grid_move = (int)(g < 1 ? 1 : g);
+    }
     {
-        int64_t t1 = scan_tiles(n), t2 = scan_tiles(n + 1);
-        f->grid_scan = (int)(t1 < kMaxGrid ? t1 : kMaxGrid);
+        int64_t t2 = scan_tiles(n + 1);
         f->grid_scan2 = (int)(t2 < kMaxGrid ? t2 : kMaxGrid);
     }
     *out = f;

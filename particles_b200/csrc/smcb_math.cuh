@@ -14,12 +14,41 @@ namespace smcb {
 
 constexpr double kRintMagic = 6755399441055744.0;  // 1.5 * 2^52: x + magic rounds x to nearest int
 
+#ifndef SMCB_ESTRIN
+#define SMCB_ESTRIN 0
+#endif
+// polynomial evaluation: Horner (N-1 dependent FMAs) or Estrin (depth ~log2 N, a few more
+// multiplies) -- the latter shortens the dependent fp64 chains the step kernel waits on
 template <int N>
 __device__ __forceinline__ double horner(const double (&c)[N], double x) {
+#if SMCB_ESTRIN
+    constexpr int H = (N + 1) / 2;
+    double q[H];
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) q[i] = fma(c[2 * i + 1], x, c[2 * i]);
+    if (N & 1) q[H - 1] = c[N - 1];
+    double xp = x * x;
+    int m = H;
+#pragma unroll
+    for (int level = 0; level < 5; level++) {
+        if (m > 1) {
+            const int h = (m + 1) / 2;
+#pragma unroll
+            for (int i = 0; i < H / 2 + 1; i++) {
+                if (i < m / 2) q[i] = fma(q[2 * i + 1], xp, q[2 * i]);
+            }
+            if (m & 1) q[h - 1] = q[m - 1];
+            xp = xp * xp;
+            m = h;
+        }
+    }
+    return q[0];
+#else
     double p = c[N - 1];
 #pragma unroll
     for (int i = N - 2; i >= 0; i--) p = fma(p, x, c[i]);
     return p;
+#endif
 }
 
 // exp(x): x <= ~709; returns 0 for x < -708 (incl. -inf; the lost range is < 3e-308),
@@ -36,6 +65,18 @@ __device__ __forceinline__ double fexp(double x) {
     res = (x < -708.0) ? 0.0 : res;
     res = (x > 709.0) ? CUDART_INF : res;
     return res;
+}
+
+// exp(x) for x <= 0 (weights relative to their maximum): no overflow branch
+__device__ __forceinline__ double fexp_neg(double x) {
+    const double t = fma(x, SMCB_LOG2E, kRintMagic);
+    const double kd = t - kRintMagic;
+    const int k = __double2loint(t);
+    double r = fma(kd, -SMCB_LN2_HI, x);
+    r = fma(kd, -SMCB_LN2_LO, r);
+    const double p = horner(kExpC, r);
+    const double res = p * __hiloint2double((k + 1023) << 20, 0);
+    return (x < -708.0) ? 0.0 : res;
 }
 
 // log(x) for positive NORMAL x (the 53-bit uniforms of box_muller are >= 2^-54)
@@ -84,8 +125,7 @@ __device__ __forceinline__ void box_muller_fast(const uint32_t r[4], double &z0,
 __device__ __forceinline__ void normal_pair_fast(const Philox &key, uint64_t pair, uint32_t t,
                                                  uint32_t comp, double &z0, double &z1) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), t, (comp << 8) | kPurposeNormal, key.k0,
-                  key.k1, r);
+    philox4x32_10k((uint32_t)pair, (uint32_t)(pair >> 32), t, (comp << 8) | kPurposeNormal, key, r);
     box_muller_fast(r, z0, z1);
 }
 
@@ -101,7 +141,7 @@ __device__ __forceinline__ void lse3_add_batch(Lse3 &a, const double (&v)[NV]) {
 #pragma unroll
     for (int j = 1; j < NV; j++) mb = fmax(mb, v[j]);
     if (mb > a.m) {                       // also the first time (a.m = -inf): fexp(-inf) = 0
-        const double r = fexp(a.m - mb);
+        const double r = fexp_neg(a.m - mb);
         a.s *= r;
         a.q *= r * r;
         a.m = mb;
@@ -109,7 +149,7 @@ __device__ __forceinline__ void lse3_add_batch(Lse3 &a, const double (&v)[NV]) {
     if (a.m == -CUDART_INF) return;       // nothing but -inf so far
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const double e = fexp(v[j] - a.m);
+        const double e = fexp_neg(v[j] - a.m);
         a.s += e;
         a.q = fma(e, e, a.q);
     }

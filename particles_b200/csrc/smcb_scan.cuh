@@ -3,14 +3,14 @@
 //
 // Decoupled look-back (Merrill & Garland 2016) with two changes that make the
 // result a pure function of the input:
-//   * tiles publish only their AGGREGATE; prefixes are rebuilt from aggregates with
-//     a fixed association: groups of 32 consecutive tiles are summed by a warp scan,
-//     group prefixes C_g are chained sequentially (C_{g+1} = C_g + S_g).  A tile may
-//     pick up an already-published C_k as a shortcut, but the value it would have
-//     computed itself is bit-identical, so timing never changes a bit of the output.
-//   * every level (thread, warp, block, group) clamps its values into the interval
-//     spanned by its own base and the base of its successor, which makes the output
-//     non-decreasing BY CONSTRUCTION.  np.searchsorted on it is then well defined and
+//   * the exclusive prefix of tile t is DEFINED with a fixed (sequential) association over
+//     the tile aggregates:  P_0 = 0,  P_{t+1} = fl(P_t + a_t).  A tile takes the nearest
+//     already-published P_k as a shortcut and adds a_k .. a_{t-1} in order, so whichever k
+//     it finds, it computes the same bits: timing never changes the output.  Every tile
+//     publishes P_t and P_{t+1} as soon as it has them, so k is normally within a few tiles.
+//   * every level (thread, warp, block) clamps its values into the interval spanned by its
+//     own base and the base of its successor (tile level: [P_t, P_{t+1}]), which makes the
+//     output non-decreasing BY CONSTRUCTION.  np.searchsorted on it is then well defined and
 //     the search kernel can be held to it bit-exactly.
 #pragma once
 #include "smcb_common.cuh"
@@ -19,18 +19,18 @@ namespace smcb {
 
 constexpr int kScanItems = 8;                       // fp64 values per thread
 constexpr int kScanTile = kBlock * kScanItems;      // 2048 values per tile
-constexpr int kScanGroup = 32;                      // tiles per look-back group
+
 
 struct ScanState {          // lives in the context workspace, reset to 0xFF.. per launch
     unsigned int *ticket;   // dynamic tile id (starts at 0xFFFFFFFF -> first tile is 0)
-    unsigned long long *agg;   // [tiles]   tile aggregates (bit pattern of a double)
-    unsigned long long *cpref; // [groups+1] group prefixes C_g
+    unsigned long long *agg;   // [tiles]     tile aggregates a_t (bit pattern)
+    unsigned long long *cpref; // [tiles + 1] exclusive tile prefixes P_t
 };
 
 inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
 inline size_t scan_state_bytes(int64_t n) {
     int64_t t = scan_tiles(n);
-    return 16 + 8 * (size_t)t + 8 * (size_t)(t / kScanGroup + 2);
+    return 16 + 8 * (size_t)t + 8 * (size_t)(t + 2);
 }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
@@ -114,67 +114,49 @@ __device__ __forceinline__ void scan_tiles_loop(const LOAD &load, int64_t n, T *
         if (tid == kBlock - 1)                                    // publish the tile aggregate
             *reinterpret_cast<volatile unsigned long long *>(st.agg + tile) = canon_bits(incl);
 
-        // look-back: warp 0 rebuilds this tile's exclusive prefix P_t and P_{t+1}
+        // look-back: warp 0 obtains this tile's exclusive prefix P_t and P_{t+1} = fl(P_t + a_t)
         if (warp == 0) {
-            const unsigned int g = tile / kScanGroup, rr = tile % kScanGroup;
-            // (1) nearest published group prefix C_k, k <= g: 32 candidates per probe round
-            //     (lane l looks at C_{base-l}); C_0 = 0 is published by definition.
-            unsigned int k = 0;
             T c = 0;
-            for (int base = (int)g;; base -= 32) {
-                const int idx = base - lane;
-                unsigned long long b = kNotReady;
-                if (idx >= 1) b = ld_volatile_u64(st.cpref + idx);
-                else if (idx == 0) b = canon_bits((T)0);
-                const unsigned int ready = __ballot_sync(0xffffffffu, b != kNotReady);
-                if (ready) {
-                    const int first = __ffs(ready) - 1;          // smallest lane = largest index
-                    k = (unsigned int)(base - first);
-                    c = from_bits<T>(__shfl_sync(0xffffffffu, b, first));
-                    break;
-                }
-            }
-            // (2) fold whole groups k .. g-1 (all their tiles precede ours): the loads of up to
-            //     4 groups are issued together, the fold itself is sequential in a fixed order.
-            for (; k < g; k += 4) {
-                unsigned long long b4[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    b4[i] = (k + i < g) ? ld_volatile_u64(st.agg + (size_t)(k + i) * kScanGroup + lane) : 0ull;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (k + i < g) {
-                        while (b4[i] == kNotReady)
-                            b4[i] = ld_volatile_u64(st.agg + (size_t)(k + i) * kScanGroup + lane);
-                        T sg = warp_scan_monotone(from_bits<T>(b4[i]), lane);
-                        sg = __shfl_sync(0xffffffffu, sg, 31);
-                        c = c + sg;
-                        if (lane == 0)
-                            *reinterpret_cast<volatile unsigned long long *>(st.cpref + k + i + 1) = canon_bits(c);
+            if (tile > 0) {
+                // (1) nearest published prefix P_k, k <= tile (P_0 = 0 by definition); lane l probes
+                //     index base - l, several windows back if need be
+                long long k = 0;
+                for (long long base = (long long)tile;; base -= 32) {
+                    const long long idx = base - lane;
+                    unsigned long long b = kNotReady;
+                    if (idx >= 1) b = ld_volatile_u64(st.cpref + idx);
+                    else if (idx == 0) b = canon_bits((T)0);
+                    const unsigned int ready = __ballot_sync(0xffffffffu, b != kNotReady);
+                    if (ready) {
+                        const int first = __ffs(ready) - 1;      // smallest lane = largest index
+                        k = base - first;
+                        c = from_bits<T>(__shfl_sync(0xffffffffu, b, first));
+                        break;
                     }
                 }
+                // (2) c = (((P_k + a_k) + a_{k+1}) + ...) + a_{tile-1}: strictly sequential adds
+                for (long long j0 = k; j0 < (long long)tile; j0 += 32) {
+                    const long long j = j0 + lane;
+                    unsigned long long b = 0ull;
+                    if (j < (long long)tile) {
+                        do { b = ld_volatile_u64(st.agg + j); } while (b == kNotReady);
+                    }
+                    const T aj = from_bits<T>(b);
+                    const int cnt = (int)(((long long)tile - j0) < 32 ? ((long long)tile - j0) : 32);
+                    for (int l = 0; l < cnt; l++) c = c + __shfl_sync(0xffffffffu, aj, l);
+                }
             }
-            T a = 0;
-            if ((unsigned int)lane < rr) {
-                unsigned long long b;
-                do { b = ld_volatile_u64(st.agg + (size_t)g * kScanGroup + lane); } while (b == kNotReady);
-                a = from_bits<T>(b);
-            } else if ((unsigned int)lane == rr) {   // own aggregate: same association as `incl`
-                T own = 0;                         // of thread kBlock-1, no global round trip
-#pragma unroll
-                for (int w = 0; w < kBlock / 32; w++) own = own + s_warp[w];
-                a = from_bits<T>(canon_bits(own));
-            }
-            T ig = warp_scan_monotone(a, lane);
-            T i_prev = __shfl_sync(0xffffffffu, ig, rr > 0 ? rr - 1 : 0);
-            T i_this = __shfl_sync(0xffffffffu, ig, rr);
-            T p_t = rr > 0 ? (c + i_prev) : c;
-            T p_next = c + i_this;
+            T own = 0;                                // own aggregate: same association as `incl`
+#pragma unroll                                        // of thread kBlock-1, no global round trip
+            for (int w = 0; w < kBlock / 32; w++) own = own + s_warp[w];
+            own = from_bits<T>(canon_bits(own));
+            const T p_next = c + own;
             if (lane == 0) {
-                s_pref[0] = p_t;
+                s_pref[0] = c;
                 s_pref[1] = p_next;
-                if (rr == kScanGroup - 1)
-                    *reinterpret_cast<volatile unsigned long long *>(st.cpref + g + 1) = canon_bits(p_next);
+                if (tile > 0)
+                    *reinterpret_cast<volatile unsigned long long *>(st.cpref + tile) = canon_bits(c);
+                *reinterpret_cast<volatile unsigned long long *>(st.cpref + tile + 1) = canon_bits(p_next);
             }
         }
         __syncthreads();
