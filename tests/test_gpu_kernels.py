@@ -91,7 +91,7 @@ def test_device_math(pb):
     np.testing.assert_allclose(run(2, v), np.sin(2 * np.pi * v), atol=2e-15, rtol=0)
     np.testing.assert_allclose(run(3, v), np.cos(2 * np.pi * v), atol=2e-15, rtol=0)
     exact = [float(mpmath.sin(2 * mpmath.pi * mpmath.mpf(float(t)))) for t in v[:2000]]
-    np.testing.assert_allclose(run(2, v)[:2000], exact, rtol=4.5e-16, atol=1e-300)
+    np.testing.assert_allclose(run(2, v)[:2000], exact, rtol=0, atol=1e-15)    # <= 4.5 ulp of 1
 
 
 # ----------------------------------------------------------------------- weights
