@@ -151,7 +151,8 @@ typedef struct smcb_filter smcb_filter;
 
 typedef struct {
     int32_t model, fk, scheme, dim;  /* dim = state dimension d                     */
-    int32_t dy, n_params, reserved0, reserved1;
+    int32_t dy, n_params;
+    int32_t world, rank;             /* particle shards over `world` GPUs (0/1 = one device) */
     int64_t n;                       /* particles on this device                    */
     int64_t n_global;                /* particles over all ranks (== n if 1 GPU)    */
     int64_t index_offset;            /* global index of local particle 0 (Philox)   */
@@ -170,12 +171,22 @@ typedef struct {
     const double *u_in; /* NULL, or injected uniforms: (T, n + 1)                   */
     double *scratch;    /* NULL, or n + 2 doubles (multinomial: exponential spacings) */
     const double *step_consts; /* NULL, or (T) host-computed per-step model constants */
+    double *local_stats;       /* world > 1: 8 doubles, this rank's weight statistics     */
+    const double *gathered;    /* world > 1: world x 8 doubles, filled by the all-gather  */
 } smcb_filter_desc;
 
 int smcb_filter_create(smcb_ctx *ctx, const smcb_filter_desc *desc, smcb_filter **out);
 int smcb_filter_destroy(smcb_filter *f);
 /* enqueue nsteps steps of SMC.__next__ (core.py:369-383); no host sync */
 int smcb_filter_step(smcb_filter *f, int64_t nsteps);
+/* sharded filter: particles are partitioned over `world` GPUs, one
+ * process each.  A step is step_local (this rank's kernels, ending with its (max, sum exp,
+ * sum exp^2) in desc.local_stats), ONE all-gather of 8 doubles per rank into desc.gathered
+ * done by the host layer on the same stream (NCCL), and step_finish (global log-normaliser,
+ * ESS, logLt recursion and the resampling decision, identical on every rank).  Resampling is
+ * per shard with the shard's mass carried in the restart log-weight. */
+int smcb_filter_step_local(smcb_filter *f);
+int smcb_filter_step_finish(smcb_filter *f);
 /* same, with a CUDA-event pair around every kernel launch; synchronises at the end.
  * out[0..3] = summed device ms of {init, weight-scan, spacings-scan, move} kernels,
  * out[4..7] = launches of each (bench.py "roofline") */

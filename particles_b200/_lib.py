@@ -24,13 +24,13 @@ c_dp = C.c_void_p  # device pointers travel as integers
 class FilterDesc(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("fk", C.c_int32), ("scheme", C.c_int32), ("dim", C.c_int32),
-        ("dy", C.c_int32), ("n_params", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("dy", C.c_int32), ("n_params", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
         ("n", C.c_int64), ("n_global", C.c_int64), ("index_offset", C.c_int64), ("T", C.c_int64),
         ("essrmin", C.c_double), ("seed", C.c_uint64),
         ("params", C.c_double * SMCB_MAX_PARAMS),
         ("X", c_dp * 2), ("lw", c_dp * 2), ("A", c_dp), ("cdf", c_dp), ("data", c_dp),
         ("summaries", c_dp), ("z_in", c_dp), ("u_in", c_dp), ("scratch", c_dp),
-        ("step_consts", c_dp),
+        ("step_consts", c_dp), ("local_stats", c_dp), ("gathered", c_dp),
     ]
 
 
@@ -65,6 +65,8 @@ PROTOTYPES = {
     "smcb_filter_create": (C.c_int, [C.c_void_p, C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]),
     "smcb_filter_destroy": (C.c_int, [C.c_void_p]),
     "smcb_filter_step": (C.c_int, [C.c_void_p, C.c_int64]),
+    "smcb_filter_step_local": (C.c_int, [C.c_void_p]),
+    "smcb_filter_step_finish": (C.c_int, [C.c_void_p]),
     "smcb_filter_step_timed": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_double)]),
     "smcb_filter_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }

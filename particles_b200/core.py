@@ -69,7 +69,9 @@ def _is_apf(fk):
 class _FusedEngine:
     """Owns the device buffers of one fused filter and the smcb_filter handle."""
 
-    def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0):
+    def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0,
+                 world=1, rank=0, group=None):
+        self.world, self.rank, self.group = int(world), int(rank), group
         self.ctx = context()
         self.lib = self.ctx.lib
         self.N, self.T = int(N), int(spec["data"].shape[0])
@@ -109,6 +111,11 @@ class _FusedEngine:
         d.u_in = self.u_in.data_ptr() if self.u_in is not None else None
         d.scratch = self.scratch.data_ptr() if self.scratch is not None else None
         d.step_consts = self.sc.data_ptr() if self.sc is not None else None
+        d.world, d.rank = self.world, self.rank
+        if self.world > 1:      # per-step exchange buffers of the sharded filter (8 doubles / rank)
+            self.local_stats = torch.zeros(8, **f64)
+            self.gathered = torch.zeros(8 * self.world, **f64)
+            d.local_stats, d.gathered = self.local_stats.data_ptr(), self.gathered.data_ptr()
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(self.ctx.handle, C.byref(d), C.byref(h)))
@@ -116,7 +123,14 @@ class _FusedEngine:
 
     def step(self, nsteps=1):
         self.ctx.bind_stream()
-        _lib.check(self.lib.smcb_filter_step(self.handle, int(nsteps)))
+        if self.world == 1:
+            _lib.check(self.lib.smcb_filter_step(self.handle, int(nsteps)))
+            return
+        import torch.distributed as dist
+        for _ in range(int(nsteps)):    # kernels -> one tiny all-gather (NCCL, stream-ordered) -> finish
+            _lib.check(self.lib.smcb_filter_step_local(self.handle))
+            dist.all_gather_into_tensor(self.gathered, self.local_stats, group=self.group)
+            _lib.check(self.lib.smcb_filter_step_finish(self.handle))
 
     def step_timed(self, nsteps):
         """smcb_filter_step_timed: per-kernel device milliseconds (CUDA events)."""

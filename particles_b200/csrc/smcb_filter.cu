@@ -55,6 +55,10 @@ struct FilterArgs {
     unsigned int *ticket;
     ScanState scan, scan2;
     int64_t n, n_global, index_offset, T;
+    int world, rank;      // particle shards over `world` GPUs (1 = single device)
+    int grid;             // blocks of the step kernel (= number of partials / tile prefixes)
+    double *local_stats;  // world > 1: this rank's {w.m, w.s, w.q, 0, aux.m, aux.s, aux.q, 0}
+    const double *gathered;  // world > 1: all ranks' local_stats, rank-major, after the all-gather
     int64_t chunk;        // pairs of particles per block (blocked assignment, multiple of kBlock)
     double *tile_pref;    // (grid + 1) exclusive prefixes of the blocks' normalised weight mass
     double essrmin;
@@ -72,8 +76,10 @@ __device__ __forceinline__ StepK step_consts(const FilterArgs &a, long long t) {
 
 // compute_summaries (core.py:351-367) + time_to_resample for the next step (core.py:181-183)
 // executed by the whole last block; thread 0 owns the scalar work.
+// w / aux: statistics over ALL particles (all ranks); wl / xl: over this rank's shard.
 template <bool APF>
-__device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w, const Lse3 &aux) {
+__device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w, const Lse3 &aux,
+                                              const Lse3 &wl, const Lse3 &auxl) {
     __shared__ int s_next_flag;
     if (threadIdx.x == 0) {
         FilterDev *st = a.st;
@@ -90,10 +96,20 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
         st->wm = w.m; st->ws = w.s; st->wq = w.q;
         st->last_rs = st->rs_flag;
         const Lse3 &x = APF ? aux : w;
-        st->am = x.m; st->as = x.s; st->aq = x.q;
+        const Lse3 &xl = APF ? auxl : wl;
+        // the CDF of a resampling step is built from this shard's own (auxiliary) weights
+        st->am = xl.m; st->as = xl.s; st->aq = xl.q;
         double lm_aux, ess_aux;
         weights_scalars(x, N, lm_aux, ess_aux);
-        if (APF) st->reset_c = log(x.s) + x.m - log(w.s) - w.m;   // core.py:302 in closed form
+        // log-weight every resampled particle restarts from (minus logeta[A] for an APF):
+        //   single device, non-APF : 0                       (Weights(), core.py:305)
+        //   single device, APF     : log_mean_exp(logetat, W) (core.py:302) = LSE(aux) - LSE(w)
+        //   sharded                : LSE_shard(aux) - LSE_all(w) + log(world): each shard resamples
+        //                            locally and carries its share of the mass
+        double rc = 0.0;
+        if (APF || a.world > 1)
+            rc = (log(xl.s) + xl.m) - (log(w.s) + w.m) + log((double)a.world);
+        st->reset_c = rc;
         int flag = (t + 1 < a.T) && (ess_aux < N * a.essrmin);    // strict <, NaN -> False
         st->rs_flag = flag;
         st->cur ^= 1;
@@ -107,7 +123,7 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
         // P_0 = 0 <= P_1 <= ... <= P_G here (fixed order, monotone), and the scan kernel needs
         // no look-back at all.
         __shared__ double s_w[kBlock / 32];
-        const int G = (int)gridDim.x, K = APF ? 2 : 1, j = APF ? 1 : 0;
+        const int G = a.grid, K = APF ? 2 : 1, j = APF ? 1 : 0;
         const double xm = a.st->am, xs = a.st->as;
         const int per = (G + kBlock - 1) / kBlock;
         const int b0 = threadIdx.x * per;
@@ -143,6 +159,15 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
             unsigned long long *q = reinterpret_cast<unsigned long long *>(a.scan2.ticket);
             for (int64_t i = threadIdx.x; i < words2; i += blockDim.x) q[i] = kNotReady;
         }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void publish_local(const FilterArgs &a, const Lse3 (&tot)[K]) {
+    if (threadIdx.x == 0) {
+        double *o = a.local_stats;
+        o[0] = tot[0].m; o[1] = tot[0].s; o[2] = tot[0].q; o[3] = 0.0;
+        o[4] = tot[K - 1].m; o[5] = tot[K - 1].s; o[6] = tot[K - 1].q; o[7] = 0.0;
     }
 }
 
@@ -194,7 +219,8 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
     Lse3 tot[K];
     if (!grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot)) return;
     if (threadIdx.x == 0) a.st->cur = 1;   // finalize flips it to 0: step 0 wrote buffers [0]
-    finalize_step<APF>(a, tot[0], tot[K - 1]);
+    if (a.world > 1) { publish_local<K>(a, tot); return; }
+    finalize_step<APF>(a, tot[0], tot[K - 1], tot[0], tot[K - 1]);
 }
 
 // ---------------------------------------------------------------------------
@@ -495,8 +521,8 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
                 if (APF) {   // core.py:302: lw = log_mean_exp(logetat, W) - logetat[A]
                     base[0] = reset_c - model.logeta(kprev, xp[0]);
                     base[1] = reset_c - model.logeta(kprev, xp[1]);
-                } else {     // Weights() then add(delta): lw = delta
-                    base[0] = 0.0; base[1] = 0.0;
+                } else {     // Weights() then add(delta): lw = 0 + delta (shard mass if sharded)
+                    base[0] = reset_c; base[1] = reset_c;
                 }
                 if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(a0, a1);
                 else a.A[2 * p] = a0;
@@ -512,7 +538,29 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
 
     Lse3 tot[K];
     if (!grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot)) return;
-    finalize_step<APF>(a, tot[0], tot[K - 1]);
+    if (a.world > 1) { publish_local<K>(a, tot); return; }
+    finalize_step<APF>(a, tot[0], tot[K - 1], tot[0], tot[K - 1]);
+}
+
+// sharded runs: after the all-gather of the per-rank statistics, one block per rank merges
+// them in rank order (identical bits on every rank) and runs the same finalize as above
+template <bool APF>
+__global__ void __launch_bounds__(kBlock) k_finish(FilterArgs a) {
+    __shared__ Lse3 s_tot[4];
+    if (threadIdx.x == 0) {
+        Lse3 w = lse3_empty(), x = lse3_empty();
+        for (int r = 0; r < a.world; r++) {
+            const double *g = a.gathered + (size_t)r * 8;
+            w = lse3_merge(w, Lse3{g[0], g[1], g[2]});
+            x = lse3_merge(x, Lse3{g[4], g[5], g[6]});
+        }
+        const double *me = a.gathered + (size_t)a.rank * 8;
+        s_tot[0] = w; s_tot[1] = x;
+        s_tot[2] = Lse3{me[0], me[1], me[2]};
+        s_tot[3] = Lse3{me[4], me[5], me[6]};
+    }
+    __syncthreads();
+    finalize_step<APF>(a, s_tot[0], APF ? s_tot[1] : s_tot[0], s_tot[2], APF ? s_tot[3] : s_tot[2]);
 }
 
 }  // namespace smcb
@@ -534,6 +582,7 @@ struct smcb_filter {
     int *timed_kind;
     int (*launch_init)(smcb_filter *);
     int (*launch_step)(smcb_filter *);
+    int (*launch_finish)(smcb_filter *);
 };
 
 template <class M, int FK, int SCHEME>
@@ -573,10 +622,19 @@ static int launch_init_t(smcb_filter *f) {
     return SMCB_OK;
 }
 
+template <int FK>
+static int launch_finish_t(smcb_filter *f) {
+    k_finish<FkTraits<FK>::apf><<<1, kBlock, 0, f->ctx->stream>>>(f->args);
+    f->ctx->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
 template <class M, int FK, int SCHEME>
 static int bind_one(smcb_filter *f) {
     f->launch_init = launch_init_t<M, FK>;
     f->launch_step = launch_step_t<M, FK, SCHEME>;
+    f->launch_finish = launch_finish_t<FK>;
     int nb = 0;
     SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_move<M, FK, SCHEME>, kBlock, 0));
     f->blocks_per_sm = nb < 1 ? 1 : nb;
@@ -704,6 +762,13 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
         g = (npairs + chunk - 1) / chunk;
         a.chunk = chunk;
         f->grid_move = (int)(g < 1 ? 1 : g);
+        a.grid = f->grid_move;
+        a.world = d->world > 1 ? d->world : 1;
+        a.rank = d->world > 1 ? d->rank : 0;
+        a.local_stats = d->local_stats;
+        a.gathered = d->gathered;
+        SMCB_REQUIRE(a.world == 1 || (d->local_stats && d->gathered && a.rank >= 0 && a.rank < a.world),
+                     "smcb_filter_create: world > 1 needs local_stats / gathered buffers and a valid rank");
     }
     {
         int64_t t2 = scan_tiles(n + 1);
@@ -721,8 +786,25 @@ extern "C" int smcb_filter_destroy(smcb_filter *f) {
     return SMCB_OK;
 }
 
+// sharded filters: one step = step_local (kernels up to the per-rank statistics), an all-gather
+// of 8 doubles per rank done by the host layer (NCCL, same stream), then step_finish
+extern "C" int smcb_filter_step_local(smcb_filter *f) {
+    SMCB_REQUIRE(f != nullptr && f->args.world > 1, "smcb_filter_step_local: not a sharded filter");
+    SMCB_REQUIRE(f->t_host < f->desc.T, "smcb_filter_step_local: all steps already done");
+    return (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
+}
+
+extern "C" int smcb_filter_step_finish(smcb_filter *f) {
+    SMCB_REQUIRE(f != nullptr && f->args.world > 1, "smcb_filter_step_finish: not a sharded filter");
+    int rc = f->launch_finish(f);
+    if (rc) return rc;
+    f->t_host++;
+    return SMCB_OK;
+}
+
 extern "C" int smcb_filter_step(smcb_filter *f, int64_t nsteps) {
     SMCB_REQUIRE(f != nullptr, "smcb_filter_step: NULL filter");
+    SMCB_REQUIRE(f->args.world == 1, "smcb_filter_step: sharded filters use step_local / step_finish");
     // host mirror of t: the device advances by exactly one per launched step
     for (int64_t i = 0; i < nsteps; i++) {
         if (f->t_host >= f->desc.T) {
@@ -743,6 +825,7 @@ extern "C" int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *ou
     SMCB_REQUIRE(f && out8, "smcb_filter_step_timed: NULL argument");
     SMCB_REQUIRE(nsteps >= 0 && nsteps <= 100000, "smcb_filter_step_timed: nsteps out of range");
     SMCB_REQUIRE(f->t_host + nsteps <= f->desc.T, "smcb_filter_step_timed: past the last step");
+    SMCB_REQUIRE(f->args.world == 1, "smcb_filter_step_timed: single-device filters only");
     cudaStream_t s = f->ctx->stream;
     const bool multi = f->desc.scheme == SMCB_RS_MULTINOMIAL;
     const int per = multi ? 3 : 2;

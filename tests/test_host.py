@@ -56,7 +56,7 @@ def test_filter_desc_layout_matches_header():
     #include "smcb.h"
     int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(smcb_filter_desc),
         offsetof(smcb_filter_desc, n), offsetof(smcb_filter_desc, params), offsetof(smcb_filter_desc, X),
-        offsetof(smcb_filter_desc, z_in), offsetof(smcb_filter_desc, step_consts)); return 0; }
+        offsetof(smcb_filter_desc, z_in), offsetof(smcb_filter_desc, gathered)); return 0; }
     '''
     exe = os.path.join(ROOT, "oracle", "_build", "layout_probe")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
@@ -65,7 +65,7 @@ def test_filter_desc_layout_matches_header():
     vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
     D = _lib.FilterDesc
     assert vals == [ctypes.sizeof(D), D.n.offset, D.params.offset, D.X.offset, D.z_in.offset,
-                    D.step_consts.offset]
+                    D.gathered.offset]
 
 
 def test_philox_known_answers():
