@@ -55,6 +55,18 @@ def hbm_peak():
     return HBM_FALLBACK_GBS, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_move launch (no-resampling step) from
+    the committed `ncu --set full` capture (profiles/*_ncu_summary.json); None if absent."""
+    import glob
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            return float(json.load(open(fn))["move"]["dram_traffic_bytes"])
+        except Exception:
+            continue
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -147,8 +159,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 16))            # ~1 GB of NumPy temporaries per worker at N=1e7
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                        # ~1.5 GB of NumPy temporaries per worker at N=1e7
+        import psutil
+        mem_workers = int(psutil.virtual_memory().available / 2.0e9)
+    except Exception:
+        mem_workers = 16
+    workers = max(1, min(cores, mem_workers, 128))
     n = N_PER_GPU
     K = max(1, min(args.steps, 4))              # bounded sample: ~3 s per step per worker
     reps = max(1, min(args.warmup, 1))
@@ -256,7 +273,7 @@ def run_b200(args):
         scan_gbs = (n * 16.0 * nrs2) / (kms["scan"] * 1e-3) / 1e9 if nrs2 else None
         roof = {"bound": "hbm", "kernel": "k_move<StochVol,Bootstrap,systematic>",
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": ncu_traffic(),
                 "avg_launch_us": 1e3 * move_ms / max(1, kcnt["move"]),
                 "algorithmic_bytes_per_particle": {"no_resample": 32, "resample": 40, "scan": 16},
                 "scan_kernel": {"achieved": scan_gbs, "launches_doing_work": nrs2,
@@ -279,6 +296,23 @@ def run_b200(args):
                "d2h_bytes_per_step": 32, "seconds": dt, "logLt": ll,
                "api": "particles_b200.SMC(fk=Bootstrap(StochVol(), data), N).run()"}
 
+    if world > 1:       # end to end through the public sharded API, every rank takes part
+        from particles_b200.parallel import ShardedSMC
+        y_host = [np.atleast_1d(v) for v in y[:K]]
+        barrier()
+        t0 = time.perf_counter()
+        sp = ShardedSMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y_host), N=n, resampling=SCHEME,
+                        ESSrmin=ESSRMIN, seed=77)
+        sp.run()
+        ll = sp.logLt
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": n * world * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8,
+               "d2h_bytes_per_step": 32, "seconds": dt, "logLt": ll,
+               "api": "particles_b200.parallel.ShardedSMC(fk=Bootstrap(StochVol(), data), N).run() on every rank"}
+        sp._engine.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

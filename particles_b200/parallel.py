@@ -34,6 +34,41 @@ class ShardedFilter(_FusedEngine):
                          world=world, rank=rank, group=group)
 
 
+class ShardedSMC:
+    """Public entry point for a particle-sharded run (call it from every rank of an initialised
+    ``torch.distributed`` NCCL group): ``ShardedSMC(fk=..., N=<particles on THIS rank>).run()``.
+    ``N_global = world * N``.  Stock (fused) models only."""
+
+    def __init__(self, fk=None, N=100, resampling="systematic", ESSrmin=0.5, seed=0, group=None):
+        import time
+        import torch.distributed as dist
+        from .state_space_models import fused_spec
+        spec = fused_spec(fk)
+        if spec is None or resampling == "residual":
+            raise NotImplementedError("sharded runs need a fused model and a fused resampling scheme")
+        self.fk, self.N = fk, N
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._time = time
+        self._engine = ShardedFilter(spec, N, resampling, ESSrmin, seed, self.rank, self.world, group)
+        self.t, self.logLt, self.cpu_time = 0, 0.0, None
+        self.ESSs, self.logLts, self.rs_flags = [], [], []
+
+    def run(self):
+        t0 = self._time.perf_counter()
+        T = self._engine.T
+        self._engine.step(T - self.t)
+        table = self._engine.summ.cpu().numpy()      # the one device->host read of the run
+        self.ESSs = [float(v) for v in table[:, 0]]
+        self.logLts = [float(v) for v in table[:, 1]]
+        self.rs_flags = [bool(v) for v in table[:, 2]]
+        self.t, self.logLt = T, self.logLts[-1]
+        self.cpu_time = self._time.perf_counter() - t0
+
+    @property
+    def X(self):
+        return self._engine.X[(self.t - 1) & 1]
+
+
 # ---------------------------------------------------------------------------
 # host restatement of the exchange algebra (used by tests and by post-processing)
 # ---------------------------------------------------------------------------
