@@ -295,3 +295,47 @@ def test_full_size_properties_1e7(golden_stats):
     assert abs(pf.logLt - ref.logLt) < 0.08
     w = pf.wgts
     assert 1 <= w.ESS <= N and abs(float(w.W.sum().item()) - 1) < 1e-10
+
+
+# ------------------------------------------------------------------ d-dimensional models
+def test_plugin_bearings_only_vs_reference(golden_stats):
+    """BASELINE config 3 (i): BearingsOnly (IndepProd(Normal, Normal, Dirac, Dirac) state,
+    arctan bearing) through the plugin path; logLt against the reference's own runs."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    yb = golden_stats["data/bearings_seed0_T40"]
+    ref = golden_stats["stat/bearings_T40_N20000_boot/logLt"]
+    mu, sd = ref.mean(), ref.std(ddof=1)
+    out = []
+    for s in range(4):
+        pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.BearingsOnly(), data=list(yb.reshape(-1, 1))), N=20_000,
+                    resampling="stratified", seed=s)
+        assert not pf.fused
+        pf.run()
+        out.append(pf.logLt)
+        assert pf.X.shape == (20_000, 4)
+    out = np.array(out)
+    assert abs(out.mean() - mu) < 4 * sd * np.sqrt(1 / 4 + 1 / len(ref)) + 1e-6, (out, mu, sd)
+    assert 0.2 * sd < out.std(ddof=1) < 5 * sd
+
+
+@pytest.mark.parametrize("fkname", ["boot", "guided", "apf"])
+def test_plugin_mvlingauss_exact_kalman(golden, golden_stats, fkname):
+    """BASELINE config 3 (ii): 4-D MvNormal model of Guarniero et al with the optimal proposal;
+    exact Kalman log-likelihood + the reference's Monte-Carlo spread at N = 1e4."""
+    import particles_b200 as pb
+    from particles_b200 import kalman, state_space_models as ssm
+    ym = golden_stats["data/mvlg_seed5_T30"]
+    exact = float(np.sum(golden["kalman/mvlg_logpyt"]))
+    ref = golden_stats[f"stat/mvlg_T30_N10000_{fkname}/logLt"]
+    sd = ref.std(ddof=1)
+    mv = kalman.MVLinearGauss_Guarniero_etal(alpha=0.4, dx=4)
+    out = []
+    for s in range(4):
+        pf = pb.SMC(fk=getattr(ssm, FK[fkname][0])(ssm=mv, data=list(ym)), N=10_000,
+                    resampling="stratified", seed=10 + s)
+        pf.run()
+        out.append(pf.logLt)
+    out = np.array(out)
+    assert abs(out.mean() - exact) < 4 * sd / 2 + sd ** 2 + 1e-3, (out, exact, sd)
+    assert abs(out.mean() - ref.mean()) < 4 * sd * np.sqrt(1 / 4 + 1 / len(ref)) + 1e-3
