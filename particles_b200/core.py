@@ -76,9 +76,11 @@ class _FusedEngine:
         self.lib = self.ctx.lib
         self.N, self.T = int(N), int(spec["data"].shape[0])
         n, T = self.N, self.T
+        self.dim, self.dy = int(spec.get("dim", 1)), int(spec.get("dy", 1))
         dev = self.ctx.device
         f64 = dict(dtype=torch.float64, device=dev)
-        self.X = [torch.empty(n, **f64), torch.empty(n, **f64)]
+        xshape = (n,) if self.dim == 1 else (self.dim, n)      # SoA: component-major
+        self.X = [torch.empty(xshape, **f64), torch.empty(xshape, **f64)]
         self.lw = [torch.empty(n, **f64), torch.empty(n, **f64)]
         self.A = torch.empty(n, dtype=torch.int64, device=dev)
         self.cdf = torch.empty(n, **f64)
@@ -96,8 +98,8 @@ class _FusedEngine:
             self.z_in = None if z is None else as_device(z)
             self.u_in = None if u is None else as_device(u)
         d = _lib.FilterDesc()
-        d.model, d.fk, d.scheme, d.dim = spec["model"], spec["fk"], _lib.RS_CODES[scheme], 1
-        d.dy, d.n_params = 1, len(spec["params"])
+        d.model, d.fk, d.scheme, d.dim = spec["model"], spec["fk"], _lib.RS_CODES[scheme], self.dim
+        d.dy, d.n_params = self.dy, len(spec["params"])
         d.n, d.n_global = n, int(n_global or n)
         d.index_offset, d.T = int(index_offset), T
         d.essrmin, d.seed = float(ESSrmin), int(seed) & (2 ** 64 - 1)
@@ -222,7 +224,10 @@ class SMC:
     def X(self):
         if not self.fused:
             return self._p["X"]
-        return None if self._done == 0 else self._engine.X[self._cur()]
+        if self._done == 0:
+            return None
+        x = self._engine.X[self._cur()]
+        return x if x.ndim == 1 else x.t()          # (N, d) view of the SoA buffer
 
     @X.setter
     def X(self, v):
@@ -273,12 +278,12 @@ class SMC:
             return None
         prev = self._engine.X[self._cur() ^ 1]
         if not self.rs_flag:
-            return prev
+            return prev if prev.ndim == 1 else prev.t()
         out = torch.empty_like(prev)
         ctx = self._engine.ctx
-        _lib.check(ctx.lib.smcb_gather(ctx.handle, ptr(prev), self.N, ptr(self._engine.A), self.N, 1,
-                                       ptr(out)))
-        return out
+        _lib.check(ctx.lib.smcb_gather(ctx.handle, ptr(prev), self.N, ptr(self._engine.A), self.N,
+                                       self._engine.dim, ptr(out)))
+        return out if out.ndim == 1 else out.t()
 
     @property
     def wgts(self):

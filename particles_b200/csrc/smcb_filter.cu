@@ -55,6 +55,7 @@ struct FilterArgs {
     unsigned int *ticket;
     ScanState scan, scan2;
     int64_t n, n_global, index_offset, T;
+    int dy;               // observation dimension
     int world, rank;      // particle shards over `world` GPUs (1 = single device)
     int grid;             // blocks of the step kernel (= number of partials / tile prefixes)
     double *local_stats;  // world > 1: this rank's {w.m, w.s, w.q, 0, aux.m, aux.s, aux.q, 0}
@@ -68,8 +69,13 @@ struct FilterArgs {
 __device__ __forceinline__ StepK step_consts(const FilterArgs &a, long long t) {
     StepK k;
     k.t = t;
-    k.y = a.data[t];
-    k.y_next = (t + 1 < a.T) ? a.data[t + 1] : 0.0;
+#pragma unroll
+    for (int i = 0; i < kMaxDy; i++) {
+        k.yv[i] = (i < a.dy) ? a.data[t * a.dy + i] : 0.0;
+        k.yn[i] = (i < a.dy && t + 1 < a.T) ? a.data[(t + 1) * a.dy + i] : 0.0;
+    }
+    k.y = k.yv[0];
+    k.y_next = k.yn[0];
     k.sc0 = a.sc ? a.sc[t] : 0.0;
     return k;
 }
@@ -190,26 +196,33 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
     const bool has_next = APF && a.T > 1;
     const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
     const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+    constexpr int D = M::D, NZ = M::NZ;
     for (int64_t p = pstart + threadIdx.x; p < pend; p += kBlock) {
-        double z[2], x[2], l[2], av[2];
-        if (a.z_in) {
-            z[0] = a.z_in[2 * p];
-            z[1] = (2 * p + 1 < n) ? a.z_in[2 * p + 1] : 0.0;
-        } else {
-            normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, 0u, z[0], z[1]);
+        double z[2][NZ], x[2][D], l[2], av[2];
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            if (a.z_in) {                                  // injected normals: (T, NZ, n)
+                const double *zz = a.z_in + (size_t)c * n;
+                z[0][c] = zz[2 * p];
+                z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
+            } else {
+                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, (uint32_t)c, z[0][c], z[1][c]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             double d;
-            fk_init<M, FK>(model, k, z[j], x[j], d);
+            model_init<M, FK>(model, k, z[j], x[j], d);
             l[j] = fix_nan(d);
-            av[j] = has_next ? fix_nan(l[j] + model.logeta(k, x[j])) : -CUDART_INF;
+            av[j] = has_next ? fix_nan(l[j] + model_logeta<M>(model, k, x[j])) : -CUDART_INF;
         }
         if (2 * p + 1 < n) {
-            st2(Xo + 2 * p, x[0], x[1]);
+#pragma unroll
+            for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
             st2(lwo + 2 * p, l[0], l[1]);
         } else {
-            Xo[2 * p] = x[0];
+#pragma unroll
+            for (int c = 0; c < D; c++) Xo[(size_t)c * n + 2 * p] = x[0][c];
             lwo[2 * p] = l[0];
             l[1] = -CUDART_INF; av[1] = -CUDART_INF;   // masked slot contributes exactly 0
         }
@@ -229,30 +242,41 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
 template <class M, int FK>
 struct LoadWeights {
     const double *lw, *X;
+    int64_t ntot;  // particles on this device (SoA component stride)
     double m, s;
     M model;
     StepK kprev;   // step t-1 with y_next = data[t]: what logeta(t-1, X) needs
     __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
         constexpr bool APF = FkTraits<FK>::apf;
-        double l[8], x[8];
+        constexpr int D = M::D;
+        double l[8], x[8][APF ? D : 1];
         if (i0 + 8 <= n) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) { double2 t = ld2(lw + i0 + j); l[j] = t.x; l[j + 1] = t.y; }
             if (APF) {
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) { double2 t = ld2(X + i0 + j); x[j] = t.x; x[j + 1] = t.y; }
+                for (int c = 0; c < D; c++) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        double2 t = ld2(X + (size_t)c * ntot + i0 + j);
+                        x[j][APF ? c : 0] = t.x; x[j + 1][APF ? c : 0] = t.y;
+                    }
+                }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 l[j] = (i0 + j < n) ? lw[i0 + j] : -CUDART_INF;
-                if (APF) x[j] = (i0 + j < n) ? X[i0 + j] : 0.0;
+                if (APF) {
+#pragma unroll
+                    for (int c = 0; c < D; c++) x[j][APF ? c : 0] = (i0 + j < n) ? X[(size_t)c * ntot + i0 + j] : 0.0;
+                }
             }
         }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             double e = l[j];
-            if (APF) e = fix_nan(e + model.logeta(kprev, x[j]));
+            if (APF) e = fix_nan(e + model_logeta<M>(model, kprev, x[j]));
             v[j] = (i0 + j < n) ? fexp(e - m) / s : 0.0;
         }
     }
@@ -267,6 +291,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_w(M model, FilterArgs a) {
     LoadWeights<M, FK> load;
     load.lw = a.lw[st->cur];
     load.X = a.X[st->cur];
+    load.ntot = a.n;
     load.m = st->am;
     load.s = st->as;
     load.model = model;
@@ -356,7 +381,7 @@ __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 #define SMCB_MINB 3
 #endif
 template <class M, int FK, int SCHEME>
-__global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs a) {
+__global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
     constexpr int K = APF ? 2 : 1;
     constexpr int kStage = 2048;                       // doubles of CDF staged per output tile
@@ -376,7 +401,7 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
     double *__restrict__ Xo = a.X[cur ^ 1];
     double *__restrict__ lwo = a.lw[cur ^ 1];
     const int64_t n = a.n, npairs = (n + 1) >> 1;
-    const double *zin = a.z_in ? a.z_in + (size_t)t * n : nullptr;
+    const double *zin = a.z_in ? a.z_in + (size_t)t * M::NZ * n : nullptr;
     const bool last_apf = APF && (t + 1 < a.T);
 
     Lse3 acc[K];
@@ -385,27 +410,35 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
 
     // propagate + reweight one pair of particles; writes x', lw'; returns lw' (and the
     // auxiliary log-weights of the next step for an APF), -inf in masked slots
-    auto do_pair = [&](int64_t p, const double (&xp)[2], const double (&base)[2], double *l,
+    constexpr int D = M::D, NZ = M::NZ;
+    auto do_pair = [&](int64_t p, const double (&xp)[2][D], const double (&base)[2], double *l,
                        double *av) {
-        double z[2], x[2];
-        if (zin) {
-            z[0] = zin[2 * p];
-            z[1] = (2 * p + 1 < n) ? zin[2 * p + 1] : 0.0;
-        } else {
-            normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, 0u, z[0], z[1]);
+        double z[2][NZ], x[2][D];
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            if (zin) {                                   // injected normals: (T, NZ, n)
+                const double *zz = zin + (size_t)c * n;
+                z[0][c] = zz[2 * p];
+                z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
+            } else {
+                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, (uint32_t)c,
+                                 z[0][c], z[1][c]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             double d;
-            fk_move<M, FK>(model, k, xp[j], z[j], x[j], d);
+            model_move<M, FK>(model, k, xp[j], z[j], x[j], d);
             l[j] = fix_nan(base[j] + d);                          // Weights.add, resampling.py:241-244
-            if (APF) av[j] = last_apf ? fix_nan(l[j] + model.logeta(k, x[j])) : -CUDART_INF;
+            if (APF) av[j] = last_apf ? fix_nan(l[j] + model_logeta<M>(model, k, x[j])) : -CUDART_INF;
         }
         if (2 * p + 1 < n) {
-            st2(Xo + 2 * p, x[0], x[1]);
+#pragma unroll
+            for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
             st2(lwo + 2 * p, l[0], l[1]);
         } else {
-            Xo[2 * p] = x[0];
+#pragma unroll
+            for (int c = 0; c < D; c++) Xo[(size_t)c * n + 2 * p] = x[0][c];
             lwo[2 * p] = l[0];
             l[1] = -CUDART_INF;
             if (APF) av[1] = -CUDART_INF;
@@ -419,15 +452,22 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
         const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
         const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
         for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kU * stride) {
-            double xp[kU][2], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1];
+            double xp[kU][2][D], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1];
 #pragma unroll
             for (int u = 0; u < kU; u++) {                        // all loads first (MLP)
                 const int64_t p = p0 + u * stride;
                 if (p < pend && 2 * p + 1 < n) {
-                    double2 tx = ld2(Xi + 2 * p), tl = ld2(lwi + 2 * p);
-                    xp[u][0] = tx.x; xp[u][1] = tx.y; base[u][0] = tl.x; base[u][1] = tl.y;
+                    double2 tl = ld2(lwi + 2 * p);
+                    base[u][0] = tl.x; base[u][1] = tl.y;
+#pragma unroll
+                    for (int c = 0; c < D; c++) {
+                        double2 tx = ld2(Xi + (size_t)c * n + 2 * p);
+                        xp[u][0][c] = tx.x; xp[u][1][c] = tx.y;
+                    }
                 } else if (p < pend) {
-                    xp[u][0] = Xi[2 * p]; xp[u][1] = 0.0; base[u][0] = lwi[2 * p]; base[u][1] = 0.0;
+                    base[u][0] = lwi[2 * p]; base[u][1] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; c++) { xp[u][0][c] = Xi[(size_t)c * n + 2 * p]; xp[u][1][c] = 0.0; }
                 }
             }
 #pragma unroll
@@ -515,12 +555,15 @@ __global__ void __launch_bounds__(kBlock, SMCB_MINB) k_move(M model, FilterArgs 
                 }
                 a0 = a0 < n - 1 ? a0 : n - 1;
                 a1 = a1 < n - 1 ? a1 : n - 1;
-                double xp[2], base[2];
-                xp[0] = __ldg(Xi + a0);
-                xp[1] = __ldg(Xi + a1);
+                double xp[2][D], base[2];
+#pragma unroll
+                for (int c = 0; c < D; c++) {                // Xp = X[A], component-wise (SoA)
+                    xp[0][c] = __ldg(Xi + (size_t)c * n + a0);
+                    xp[1][c] = __ldg(Xi + (size_t)c * n + a1);
+                }
                 if (APF) {   // core.py:302: lw = log_mean_exp(logetat, W) - logetat[A]
-                    base[0] = reset_c - model.logeta(kprev, xp[0]);
-                    base[1] = reset_c - model.logeta(kprev, xp[1]);
+                    base[0] = reset_c - model_logeta<M>(model, kprev, xp[0]);
+                    base[1] = reset_c - model_logeta<M>(model, kprev, xp[1]);
                 } else {     // Weights() then add(delta): lw = 0 + delta (shard mass if sharded)
                     base[0] = reset_c; base[1] = reset_c;
                 }
@@ -683,7 +726,8 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     SMCB_REQUIRE(d->X[0] && d->X[1] && d->lw[0] && d->lw[1] && d->A && d->cdf && d->data && d->summaries,
                  "smcb_filter_create: NULL device buffer");
     SMCB_REQUIRE((d->index_offset & 1) == 0, "smcb_filter_create: index_offset must be even");
-    SMCB_REQUIRE(d->dim == 1, "smcb_filter_create: this build fuses 1-D states only (dim=%d)", d->dim);
+    SMCB_REQUIRE(d->dim >= 1 && d->dim <= 4, "smcb_filter_create: fused kernels exist for state dimension 1..4 (dim=%d)", d->dim);
+    SMCB_REQUIRE(d->dy >= 1 && d->dy <= kMaxDy, "smcb_filter_create: observation dimension must be 1..%d", kMaxDy);
     SMCB_REQUIRE(d->essrmin >= 0.0 && d->essrmin <= 1.0, "smcb_filter_create: ESSrmin must be in [0, 1]");
     smcb_filter *f = new (std::nothrow) smcb_filter();
     SMCB_REQUIRE(f != nullptr, "smcb_filter_create: out of host memory");
@@ -704,6 +748,13 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
         case SMCB_MODEL_LINGAUSS: rc = bind_fk<LinGaussM>(f); break;
         case SMCB_MODEL_GORDON: rc = bind_fk<GordonM>(f); break;
         case SMCB_MODEL_THETALOGISTIC: rc = bind_fk<ThetaLogisticM>(f); break;
+        case SMCB_MODEL_BEARINGS: rc = bind_fk<BearingsM>(f); break;
+        case SMCB_MODEL_MVLINGAUSS:
+            if (d->dim == 2) rc = bind_fk<MvLinGaussM<2>>(f);
+            else if (d->dim == 3) rc = bind_fk<MvLinGaussM<3>>(f);
+            else if (d->dim == 4) rc = bind_fk<MvLinGaussM<4>>(f);
+            else { set_error("fused MVLinearGauss: dx must be 2, 3 or 4 (got %d)", d->dim); rc = SMCB_ENOSYS; }
+            break;
 #endif
         default:
             set_error("fused filter: model id %d is not available in the fused 1-D family", d->model);
@@ -745,6 +796,7 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     a.scan2.ticket = reinterpret_cast<unsigned int *>(sp);
     a.scan2.agg = reinterpret_cast<unsigned long long *>(sp + 16);
     a.scan2.cpref = a.scan2.agg + scan_tiles(n + 1);
+    a.dy = d->dy;
     a.n = n; a.n_global = d->n_global > 0 ? d->n_global : n;
     a.index_offset = d->index_offset; a.T = d->T;
     a.essrmin = d->essrmin;

@@ -17,10 +17,12 @@
 
 namespace smcb {
 
+constexpr int kMaxDy = 4;
 struct StepK {
-    double y;        // data[t]
+    double y;        // data[t]        (first component; the 1-D models read only this)
     double y_next;   // data[t+1] (0 at the last step; only logeta reads it)
     double sc0;      // host-computed per-step constant (model specific)
+    double yv[kMaxDy], yn[kMaxDy];   // vector observation data[t], data[t+1] (d-dimensional models)
     int64_t t;
 };
 
@@ -37,6 +39,7 @@ __device__ __forceinline__ double normal_logpdf_ls(double x, double loc, double 
 // params: 0 mu, 1 rho, 2 sigma, 3 sig0, 4 (1-rho)*mu, 5 log(sigma), 6 log(sig0)
 // ---------------------------------------------------------------------------
 struct StochVolM {
+    static constexpr int D = 1, NZ = 1;   // state dimension, normals per particle
     double mu, rho, sigma, sig0, c0, lsigma, lsig0;
     static constexpr bool has_proposal = true;
     __host__ void load(const double *p) {
@@ -85,6 +88,7 @@ struct StochVolM {
 //         12 log sqrt(sig2post), 13 sqrt(sX^2+sY^2), 14 log of 13, 15 sigmaX^2, 16 sigmaY^2
 // ---------------------------------------------------------------------------
 struct LinGaussM {
+    static constexpr int D = 1, NZ = 1;   // state dimension, normals per particle
     double rho, sX, sY, s0, lsX, lsY, ls0, s2p0, sp0, lsp0, s2p, sp, lsp, se, lse, sX2, sY2;
     static constexpr bool has_proposal = true;
     __host__ void load(const double *p) {
@@ -119,6 +123,7 @@ struct LinGaussM {
 // params: 0 a, 1 b, 2 c, 3 sigmaX, 4 log sigmaX;  step constant sc0 = d*cos(e*(t-1))
 // ---------------------------------------------------------------------------
 struct GordonM {
+    static constexpr int D = 1, NZ = 1;   // state dimension, normals per particle
     double a, b, c, sX, lsX;
     static constexpr bool has_proposal = false;
     __host__ void load(const double *p) { a = p[0]; b = p[1]; c = p[2]; sX = p[3]; lsX = p[4]; }
@@ -143,6 +148,7 @@ struct GordonM {
 // params: 0 tau0, 1 tau1, 2 tau2, 3 sigmaX, 4 sigmaY, 5 log sigmaX, 6 log sigmaY
 // ---------------------------------------------------------------------------
 struct ThetaLogisticM {
+    static constexpr int D = 1, NZ = 1;   // state dimension, normals per particle
     double tau0, tau1, tau2, sX, sY, lsX, lsY;
     static constexpr bool has_proposal = false;
     __host__ void load(const double *p) {
@@ -207,6 +213,186 @@ __device__ __forceinline__ void fk_move(const M &m, const StepK &k, double xp, d
         x = loc + scale * z;
         delta = m.obs_logpdf(k, xp, x);
     }
+}
+
+// ---------------------------------------------------------------------------
+// d-dimensional models (SoA state): small dense algebra in registers, no tensor cores
+// (a 4x4 triangular matvec is 10 FMAs).
+// ---------------------------------------------------------------------------
+
+// BearingsOnly -- particles/state_space_models.py:580-608 (Bootstrap only: the reference defines
+// no proposal).  State (x0, x1, x2, x3); PX = IndepProd(N(x0, sX), N(x1, sX), Dirac(x0 + x2),
+// Dirac(x1 + x3)); PY = Normal(arctan(x3 / x2) [+ pi if x2 < 0], sY).
+// params: 0 sigmaX, 1 sigmaY, 2 log sigmaY, 3..6 x0[4]
+struct BearingsM {
+    static constexpr int D = 4, NZ = 2;
+    static constexpr bool has_proposal = false;
+    double sX, sY, lsY, x0[4];
+    __host__ void load(const double *p) {
+        sX = p[0]; sY = p[1]; lsY = p[2];
+        for (int i = 0; i < 4; i++) x0[i] = p[3 + i];
+    }
+    __device__ __forceinline__ double obs(const StepK &k, const double *x) const {   // :603-608
+        double angle = atan(x[3] / x[2]);
+        if (x[2] < 0.0) angle += 3.14159265358979323846;
+        return normal_logpdf_ls(k.yv[0], angle, sY, lsY);
+    }
+    template <int FK>
+    __device__ __forceinline__ void init_nd(const StepK &k, const double *z, double *x, double &d) const {
+        x[0] = x0[0] + sX * z[0]; x[1] = x0[1] + sX * z[1]; x[2] = x0[2]; x[3] = x0[3];   // :589-595
+        d = obs(k, x);
+    }
+    template <int FK>
+    __device__ __forceinline__ void move_nd(const StepK &k, const double *xp, const double *z, double *x,
+                                            double &d) const {
+        x[0] = xp[0] + sX * z[0]; x[1] = xp[1] + sX * z[1];                             // :597-603
+        x[2] = xp[0] + xp[2]; x[3] = xp[1] + xp[3];
+        d = obs(k, x);
+    }
+    __device__ __forceinline__ double logeta_nd(const StepK &, const double *) const { return 0.0; }
+};
+
+// MVLinearGauss -- particles/kalman.py:296-361 (incl. MVLinearGauss_Guarniero_etal, 364-394):
+//   X_0 ~ N(mu0, cov0), X_t = F X_{t-1} + U_t, Y_t = G X_t + V_t, optimal proposal and logeta from
+//   the Kalman update with the common predictive covariance.  dx = DX (compile time), dy <= 4.
+// params (row-major): 0 dy | F[DX*DX] | G[4*DX] | LX[DX*DX] hldX | LY[16] hldY | K[DX*4] |
+//   LP[DX*DX] hldP | LE[16] hldE | mu0[DX] | L0[DX*DX] hld0 | loc0p[DX] | LP0[DX*DX] hldP0
+// (L* = lower Cholesky factors, hld* = sum log diag; K = Kalman gain; LE = chol of G covX G' + covY)
+template <int DX>
+struct MvLinGaussM {
+    static constexpr int D = DX, NZ = DX;
+    static constexpr bool has_proposal = true;
+    int dy;
+    double F[DX * DX], G[kMaxDy * DX], LX[DX * DX], hldX, LY[kMaxDy * kMaxDy], hldY, K[DX * kMaxDy],
+        LP[DX * DX], hldP, LE[kMaxDy * kMaxDy], hldE, mu0[DX], L0[DX * DX], hld0, loc0p[DX],
+        LP0[DX * DX], hldP0;
+    __host__ void load(const double *p) {
+        dy = (int)p[0]; p += 1;
+        auto take = [&](double *dst, int cnt) { for (int i = 0; i < cnt; i++) dst[i] = p[i]; p += cnt; };
+        take(F, DX * DX); take(G, kMaxDy * DX); take(LX, DX * DX); take(&hldX, 1);
+        take(LY, kMaxDy * kMaxDy); take(&hldY, 1); take(K, DX * kMaxDy); take(LP, DX * DX); take(&hldP, 1);
+        take(LE, kMaxDy * kMaxDy); take(&hldE, 1); take(mu0, DX); take(L0, DX * DX); take(&hld0, 1);
+        take(loc0p, DX); take(LP0, DX * DX); take(&hldP0, 1);
+    }
+    // loc + scale * (z @ L.T) with scale = 1 (distributions.py:946-947)
+    __device__ __forceinline__ void sample(const double *loc, const double *L, const double *z, double *x) const {
+#pragma unroll
+        for (int i = 0; i < DX; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j <= i; j++) acc += z[j] * L[i * DX + j];
+            x[i] = loc[i] + 1.0 * acc;
+        }
+    }
+    // MvNormal.logpdf (distributions.py:949-959), dimension DX
+    __device__ __forceinline__ double logpdf_x(const double *x, const double *loc, const double *L, double hld) const {
+        double zz[DX], ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < DX; i++) {
+            double acc = (x[i] - loc[i]) / 1.0;
+#pragma unroll
+            for (int j = 0; j < i; j++) acc -= L[i * DX + j] * zz[j];
+            zz[i] = acc / L[i * DX + i];
+            ss += zz[i] * zz[i];
+        }
+        return -0.5 * ss - (0.0 + hld) - (double)DX * kHalfLog2Pi;
+    }
+    // same in observation space (dimension dy <= 4, runtime)
+    __device__ __forceinline__ double logpdf_y(const double *y, const double *loc, const double *L, double hld) const {
+        double zz[kMaxDy], ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < kMaxDy; i++) {
+            if (i < dy) {
+                double acc = (y[i] - loc[i]) / 1.0;
+#pragma unroll
+                for (int j = 0; j < kMaxDy; j++) if (j < i) acc -= L[i * kMaxDy + j] * zz[j];
+                zz[i] = acc / L[i * kMaxDy + i];
+                ss += zz[i] * zz[i];
+            }
+        }
+        return -0.5 * ss - (0.0 + hld) - (double)dy * kHalfLog2Pi;
+    }
+    __device__ __forceinline__ void matvec_F(const double *xp, double *pm) const {   // xp @ F.T
+#pragma unroll
+        for (int i = 0; i < DX; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < DX; j++) acc += xp[j] * F[i * DX + j];
+            pm[i] = acc;
+        }
+    }
+    __device__ __forceinline__ void matvec_G(const double *x, double *gy) const {    // x @ G.T
+#pragma unroll
+        for (int i = 0; i < kMaxDy; i++) {
+            double acc = 0.0;
+            if (i < dy) {
+#pragma unroll
+                for (int j = 0; j < DX; j++) acc += x[j] * G[i * DX + j];
+            }
+            gy[i] = acc;
+        }
+    }
+    __device__ __forceinline__ double obs(const StepK &k, const double *x) const {   // PY, kalman.py:342-343
+        double gy[kMaxDy];
+        matvec_G(x, gy);
+        return logpdf_y(k.yv, gy, LY, hldY);
+    }
+    template <int FK>
+    __device__ __forceinline__ void init_nd(const StepK &k, const double *z, double *x, double &d) const {
+        if (FkTraits<FK>::guided) {      // proposal0 (kalman.py:351-354); logG(0) state_space_models.py:381-386
+            sample(loc0p, LP0, z, x);
+            d = logpdf_x(x, mu0, L0, hld0) + obs(k, x) - logpdf_x(x, loc0p, LP0, hldP0);
+        } else {                         // PX0 (kalman.py:336-337)
+            sample(mu0, L0, z, x);
+            d = obs(k, x);
+        }
+    }
+    template <int FK>
+    __device__ __forceinline__ void move_nd(const StepK &k, const double *xp, const double *z, double *x,
+                                            double &d) const {
+        double pm[DX];
+        matvec_F(xp, pm);                // PX loc, kalman.py:339-340
+        if (FkTraits<FK>::guided) {      // proposal, kalman.py:345-349 -> filter_step 196-229
+            double gy[kMaxDy], loc[DX];
+            matvec_G(pm, gy);
+#pragma unroll
+            for (int i = 0; i < DX; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < kMaxDy; j++) if (j < dy) acc += (k.yv[j] - gy[j]) * K[i * kMaxDy + j];
+                loc[i] = pm[i] + acc;
+            }
+            sample(loc, LP, z, x);
+            d = logpdf_x(x, pm, LX, hldX) + obs(k, x) - logpdf_x(x, loc, LP, hldP);
+        } else {
+            sample(pm, LX, z, x);
+            d = obs(k, x);
+        }
+    }
+    __device__ __forceinline__ double logeta_nd(const StepK &k, const double *x) const {   // kalman.py:356-360
+        double pm[DX], gy[kMaxDy];
+        matvec_F(x, pm);
+        matvec_G(pm, gy);
+        return logpdf_y(k.yn, gy, LE, hldE);
+    }
+};
+
+// uniform entry points for the step kernels: scalar Normal-kernel models or vector models
+template <class M, int FK>
+__device__ __forceinline__ void model_init(const M &m, const StepK &k, const double *z, double *x, double &d) {
+    if constexpr (M::D == 1) fk_init<M, FK>(m, k, z[0], x[0], d);
+    else m.template init_nd<FK>(k, z, x, d);
+}
+template <class M, int FK>
+__device__ __forceinline__ void model_move(const M &m, const StepK &k, const double *xp, const double *z,
+                                           double *x, double &d) {
+    if constexpr (M::D == 1) fk_move<M, FK>(m, k, xp[0], z[0], x[0], d);
+    else m.template move_nd<FK>(k, xp, z, x, d);
+}
+template <class M>
+__device__ __forceinline__ double model_logeta(const M &m, const StepK &k, const double *x) {
+    if constexpr (M::D == 1) return m.logeta(k, x[0]);
+    else return m.logeta_nd(k, x);
 }
 
 }  // namespace smcb

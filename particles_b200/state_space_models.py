@@ -258,8 +258,56 @@ def spec_thetalogistic(m, T):
     return {"model": _lib.MODEL_THETALOGISTIC, "params": p, "dim": 1, "proposal": False}
 
 
+def spec_bearings(m, T):
+    x0 = np.asarray(m.x0, dtype=np.float64).reshape(4)
+    p = [m.sigmaX, m.sigmaY, np.log(m.sigmaY)] + list(x0)
+    return {"model": _lib.MODEL_BEARINGS, "params": p, "dim": 4, "dy": 1, "n_noise": 2, "proposal": False}
+
+
+def _pad(M, rows, cols):
+    out = np.zeros((rows, cols))
+    M = np.atleast_2d(np.asarray(M, dtype=np.float64))
+    out[: M.shape[0], : M.shape[1]] = M
+    return out
+
+
+def spec_mvlingauss(m, T, data=None):
+    """kalman.py:296-361: all matrices of the fused kernel (csrc/smcb_models.cuh, MvLinGaussM) are
+    computed here with NumPy exactly as the reference's closures compute them per step."""
+    dx, dy = int(m.dx), int(m.dy)
+    if not (2 <= dx <= 4 and 1 <= dy <= 4):
+        return None
+    F, G = np.asarray(m.F, float), np.asarray(m.G, float)
+    covX, covY, cov0, mu0 = (np.asarray(v, float) for v in (m.covX, m.covY, m.cov0, m.mu0))
+
+    def chol(c):
+        L = np.linalg.cholesky(c)
+        return L, float(np.sum(np.log(np.diag(L))))
+
+    def update(pred_cov):                      # filter_step, kalman.py:196-229
+        dpc = G @ pred_cov @ G.T + covY
+        gain = np.linalg.solve(dpc, (pred_cov @ G.T).T).T
+        return dpc, gain, pred_cov - gain @ G @ pred_cov
+
+    dpc, K, fcov = update(covX)
+    dpc0, K0, fcov0 = update(cov0)
+    LX, hX = chol(covX); LY, hY = chol(covY); LP, hP = chol(fcov); LE, hE = chol(dpc)
+    L0, h0 = chol(cov0); LP0, hP0 = chol(fcov0)
+    y0 = np.zeros(dy) if data is None else np.asarray(data[0], float).reshape(-1)
+    loc0p = mu0 + (y0 - mu0 @ G.T) @ K0.T       # proposal0 (kalman.py:351-354)
+    p = [float(dy)]
+    p += list(F.reshape(-1)) + list(_pad(G, 4, dx).reshape(-1)) + list(LX.reshape(-1)) + [hX]
+    p += list(_pad(LY, 4, 4).reshape(-1)) + [hY] + list(_pad(K, dx, 4).reshape(-1))
+    p += list(LP.reshape(-1)) + [hP] + list(_pad(LE, 4, 4).reshape(-1)) + [hE]
+    p += list(mu0.reshape(-1)) + list(L0.reshape(-1)) + [h0] + list(loc0p.reshape(-1))
+    p += list(LP0.reshape(-1)) + [hP0]
+    return {"model": _lib.MODEL_MVLINGAUSS, "params": p, "dim": dx, "dy": dy, "n_noise": dx,
+            "proposal": True}
+
+
 _SPECS = {"StochVol": spec_stochvol, "LinearGauss": spec_lingauss, "Gordon_etal": spec_gordon,
-          "ThetaLogistic": spec_thetalogistic}
+          "ThetaLogistic": spec_thetalogistic, "BearingsOnly": spec_bearings,
+          "MVLinearGauss": spec_mvlingauss, "MVLinearGauss_Guarniero_etal": spec_mvlingauss}
 
 
 def fused_spec(fk):
@@ -277,11 +325,13 @@ def fused_spec(fk):
     make = _SPECS.get(type(ssm).__name__)
     if make is None:
         return None
-    spec = make(ssm, fk.T)
+    spec = make(ssm, fk.T, fk.data) if make is spec_mvlingauss else make(ssm, fk.T)
+    if spec is None:
+        return None
     if kind != _lib.FK_BOOTSTRAP and not spec["proposal"]:
         return None
     if kind == _lib.FK_GUIDED and type(ssm).__name__ == "ThetaLogistic":
         return None
     spec["fk"] = kind
-    spec["data"] = _flat_data(fk.data, 1)
+    spec["data"] = _flat_data(fk.data, spec.get("dy", 1))
     return spec
