@@ -175,8 +175,6 @@ class SMC:
         _lib.load()
         if qmc:
             raise NotImplementedError("SQMC (qmc=True) is outside the accelerated path")
-        if store_history is not False:
-            raise NotImplementedError("store_history is not available on the device path yet")
         if resampling not in rs.rs_funcs:
             raise ValueError(f"{resampling} is not a valid resampling scheme")
         self.fk, self.N, self.qmc = fk, N, qmc
@@ -184,7 +182,6 @@ class SMC:
         self.t = 0
         self._done = 0        # completed steps (== t outside of a step; collectors see t = index)
         self.cpu_time = None
-        self.hist = None
         self.summaries = None if collect == "off" else collectors.Summaries(collect)
         self._seed = np.random.randint(0, 2 ** 31 - 1) if seed is None else int(seed)
         self._engine = None
@@ -204,6 +201,8 @@ class SMC:
             context().seed(self._seed)
             self._p = {"rs_flag": False, "logLt": 0.0, "wgts": rs.Weights(), "aux": None,
                        "X": None, "Xp": None, "A": None}
+        from . import smoothing
+        self.hist = smoothing.generate_hist_obj(store_history, self)   # smoothing.py:151-161
 
     # ------------------------------------------------------------------ fused
     @property
@@ -366,6 +365,8 @@ class SMC:
         p["logLt"] += p["loglt"]
         if self.verbose:
             print(self)
+        if self.hist:
+            self.hist.save(self)
         if self.summaries:
             self.summaries.collect(self)
 
@@ -379,6 +380,8 @@ class SMC:
             self._done += 1
             if self.verbose:
                 print(self)
+            if self.hist:
+                self.hist.save(self)              # core.py:362-363 (before the collectors)
             if self.summaries:
                 self.summaries.collect(self)      # smc.t is still the index of this step
             self.t += 1
@@ -403,8 +406,9 @@ class SMC:
         """Run until completion (core.py:391-409); ``cpu_time`` is the wall time of this
         call, device work included (utils.timer semantics, utils.py:81-89)."""
         t0 = time.perf_counter()
-        if self.fused and not self.verbose and (self.summaries is None or self.summaries.only_defaults) \
-                and type(self.fk).done is FeynmanKac.done:
+        if self.fused and not self.verbose and not self.hist \
+                and (self.summaries is None or self.summaries.only_defaults) \
+                and getattr(getattr(type(self.fk), "done", None), "__qualname__", "") == "FeynmanKac.done":
             T = self._engine.T
             first = self.t
             if first < T:

@@ -542,8 +542,15 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
                 if (covered) {
                     int l0 = (int)(lo - sbase), h0 = cnt;
                     while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < su[0]) l0 = mid + 1; else h0 = mid; }
+                    // su[1] >= su[0] and on average one CDF entry per output: walk forward a few
+                    // entries before falling back to bisection (same result as searchsorted)
                     int l1 = l0, h1 = cnt;
-                    while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < su[1]) l1 = mid + 1; else h1 = mid; }
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if (l1 < cnt && s_cdf[l1] < su[1]) l1++;
+                    if (l1 < cnt && s_cdf[l1] < su[1]) {
+                        while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < su[1]) l1 = mid + 1; else h1 = mid; }
+                    }
                     a0 = sbase + l0;
                     a1 = sbase + l1;
                     if (2 * p == k1) s_hi = a0;

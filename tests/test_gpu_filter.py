@@ -433,3 +433,43 @@ def test_fused_bearings_vs_reference(golden_stats):
         out.append(pf.logLt)
     out = np.array(out)
     assert abs(out.mean() - ref.mean()) < 4 * ref.std(ddof=1) * np.sqrt(1 / 4 + 1 / len(ref)) + 1e-6
+
+
+def test_history_and_moments_collectors(golden):
+    """Boundary consumers of the step loop: store_history (rolling / full /
+    partial), genealogy, and the Moments collector, on the fused path with injected noise."""
+    import particles_b200 as pb
+    from particles_b200 import collectors as col, state_space_models as ssm
+    N, T = 1000, 30
+    y = lst(golden["data/sv_seed1_T1000"][:T])
+    z, u = make_noise(N, T, "systematic", 11)
+    mk = lambda **kw: pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, ESSrmin=0.8,  # noqa: E731
+                             noise=(z, u), **kw)
+    ref = orc.SMC(orc.Bootstrap(orc.StochVol(), y), N=N, ESSrmin=0.8,
+                  noise=oracle_noise(z, u, "systematic", N), keep=True).run()
+    pf = mk(store_history=True, collect=[col.Moments()])
+    pf.run()
+    assert len(pf.hist.X) == T and len(pf.hist.A) == T and len(pf.hist.wgts) == T
+    for t in range(T):
+        assert np.array_equal(host(pf.hist.X[t]), ref.trace[t]["X"]), t          # owned copies, bit-exact
+        if t > 0:
+            assert np.array_equal(host(pf.hist.A[t]), ref.trace[t]["A"]), t
+        np.testing.assert_allclose(host(pf.hist.wgts[t].W), ref.trace[t]["W"], rtol=1e-10, atol=1e-300)
+        m = orc.wmean_and_var(ref.trace[t]["W"], ref.trace[t]["X"])
+        np.testing.assert_allclose([pf.summaries.moments[t]["mean"], pf.summaries.moments[t]["var"]],
+                                   [m["mean"], m["var"]], rtol=1e-9)
+    B = host(pf.hist.compute_trajectories())
+    assert B.shape == (T, N) and np.array_equal(B[-1], np.arange(N))
+    Bref = [np.arange(N)]
+    for t in range(T - 1, 0, -1):
+        Bref.append(ref.trace[t]["A"][Bref[-1]])
+    assert np.array_equal(B, np.array(Bref[::-1]))
+    assert len(pf.hist.extract_one_trajectory()) == T
+    roll = mk(store_history=3)
+    roll.run()
+    assert roll.hist.T == 3 and np.array_equal(host(roll.hist.X[-1]), ref.X)
+    part = mk(store_history=lambda t: t % 10 == 0)
+    part.run()
+    assert sorted(part.hist.X) == [0, 10, 20]
+    with pytest.raises(ValueError):
+        mk(store_history=-2)
