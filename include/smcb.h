@@ -173,6 +173,10 @@ typedef struct {
     const double *step_consts; /* NULL, or (T) host-computed per-step model constants */
     double *local_stats;       /* world > 1: 8 doubles, this rank's weight statistics     */
     const double *gathered;    /* world > 1: world x 8 doubles, filled by the all-gather  */
+    double *mail_local;        /* world > 1, optional: this rank's peer mailbox (smcb_p2p_alloc,
+                                  2 * world * 16 doubles) -> statistics are exchanged by the
+                                  kernels themselves over NVLink and smcb_filter_step works */
+    double *mail_peer[8];      /* every rank's mailbox as mapped in THIS process (own = mail_local) */
 } smcb_filter_desc;
 
 int smcb_filter_create(smcb_ctx *ctx, const smcb_filter_desc *desc, smcb_filter **out);
@@ -187,6 +191,12 @@ int smcb_filter_step(smcb_filter *f, int64_t nsteps);
  * per shard with the shard's mass carried in the restart log-weight. */
 int smcb_filter_step_local(smcb_filter *f);
 int smcb_filter_step_finish(smcb_filter *f);
+/* peer memory for the fused exchange: alloc (zeroed) + 64-byte IPC handle to hand to the other
+ * ranks (any transport), open a peer's handle, close / free */
+int smcb_p2p_alloc(smcb_ctx *ctx, int64_t bytes, void **dev_ptr, unsigned char *handle64);
+int smcb_p2p_open(smcb_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
+int smcb_p2p_close(void *peer_ptr);
+int smcb_p2p_free(void *dev_ptr);
 /* same, with a CUDA-event pair around every kernel launch; synchronises at the end.
  * out[0..3] = summed device ms of {init, weight-scan, spacings-scan, move} kernels,
  * out[4..7] = launches of each (bench.py "roofline") */

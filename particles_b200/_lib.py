@@ -31,6 +31,7 @@ class FilterDesc(C.Structure):
         ("X", c_dp * 2), ("lw", c_dp * 2), ("A", c_dp), ("cdf", c_dp), ("data", c_dp),
         ("summaries", c_dp), ("z_in", c_dp), ("u_in", c_dp), ("scratch", c_dp),
         ("step_consts", c_dp), ("local_stats", c_dp), ("gathered", c_dp),
+        ("mail_local", c_dp), ("mail_peer", c_dp * 8),
     ]
 
 
@@ -67,6 +68,10 @@ PROTOTYPES = {
     "smcb_filter_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "smcb_filter_step_local": (C.c_int, [C.c_void_p]),
     "smcb_filter_step_finish": (C.c_int, [C.c_void_p]),
+    "smcb_p2p_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "smcb_p2p_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "smcb_p2p_close": (C.c_int, [C.c_void_p]),
+    "smcb_p2p_free": (C.c_int, [C.c_void_p]),
     "smcb_filter_step_timed": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_double)]),
     "smcb_filter_state": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
 }

@@ -70,8 +70,10 @@ class _FusedEngine:
     """Owns the device buffers of one fused filter and the smcb_filter handle."""
 
     def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0,
-                 world=1, rank=0, group=None):
+                 world=1, rank=0, group=None, p2p=False):
         self.world, self.rank, self.group = int(world), int(rank), group
+        self.p2p = bool(p2p) and self.world > 1
+        self._mail_local, self._mail_peers = None, []
         self.ctx = context()
         self.lib = self.ctx.lib
         self.N, self.T = int(N), int(spec["data"].shape[0])
@@ -118,14 +120,37 @@ class _FusedEngine:
             self.local_stats = torch.zeros(8, **f64)
             self.gathered = torch.zeros(8 * self.world, **f64)
             d.local_stats, d.gathered = self.local_stats.data_ptr(), self.gathered.data_ptr()
+            if self.p2p:
+                self._open_mailboxes(d)
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(self.ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h
 
+    def _open_mailboxes(self, d):
+        """Peer-memory exchange: every rank allocates a small mailbox, the 64-byte CUDA IPC
+        handles travel through torch.distributed once, each rank maps its peers' mailboxes."""
+        import torch.distributed as dist
+        ptr_ = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        _lib.check(self.lib.smcb_p2p_alloc(self.ctx.handle, 2 * self.world * 16 * 8, C.byref(ptr_), hbuf))
+        self._mail_local = ptr_.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
+        d.mail_local = self._mail_local
+        for r in range(self.world):
+            if r == self.rank:
+                d.mail_peer[r] = self._mail_local
+                continue
+            pp = C.c_void_p()
+            _lib.check(self.lib.smcb_p2p_open(self.ctx.handle, handles[r], C.byref(pp)))
+            self._mail_peers.append(pp.value)
+            d.mail_peer[r] = pp.value
+        dist.barrier(group=self.group)       # every mailbox is mapped before anybody writes
+
     def step(self, nsteps=1):
         self.ctx.bind_stream()
-        if self.world == 1:
+        if self.world == 1 or self.p2p:      # the whole loop is enqueued by the C side
             _lib.check(self.lib.smcb_filter_step(self.handle, int(nsteps)))
             return
         import torch.distributed as dist
@@ -152,6 +177,14 @@ class _FusedEngine:
         if getattr(self, "handle", None):
             self.lib.smcb_filter_destroy(self.handle)
             self.handle = None
+            if self._mail_local:
+                import torch.distributed as dist
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)       # nobody still writes into a mailbox
+                for pp in self._mail_peers:
+                    self.lib.smcb_p2p_close(C.c_void_p(pp))
+                self.lib.smcb_p2p_free(C.c_void_p(self._mail_local))
+                self._mail_local, self._mail_peers = None, []
 
     def __del__(self):
         try:

@@ -60,6 +60,10 @@ struct FilterArgs {
     int grid;             // blocks of the step kernel (= number of partials / tile prefixes)
     double *local_stats;  // world > 1: this rank's {w.m, w.s, w.q, 0, aux.m, aux.s, aux.q, 0}
     const double *gathered;  // world > 1: all ranks' local_stats, rank-major, after the all-gather
+    // peer-memory exchange (NVLink P2P): every rank owns a mailbox of 2 x world x 16 doubles
+    // ([parity][sender][8 stats, epoch, pad]); mail_peer[p] is rank p's mailbox mapped here.
+    double *mail_local;
+    double *mail_peer[8];
     int64_t chunk;        // pairs of particles per block (blocked assignment, multiple of kBlock)
     double *tile_pref;    // (grid + 1) exclusive prefixes of the blocks' normalised weight mass
     double essrmin;
@@ -170,10 +174,21 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
 
 template <int K>
 __device__ __forceinline__ void publish_local(const FilterArgs &a, const Lse3 (&tot)[K]) {
-    if (threadIdx.x == 0) {
-        double *o = a.local_stats;
-        o[0] = tot[0].m; o[1] = tot[0].s; o[2] = tot[0].q; o[3] = 0.0;
-        o[4] = tot[K - 1].m; o[5] = tot[K - 1].s; o[6] = tot[K - 1].q; o[7] = 0.0;
+    const double v[8] = {tot[0].m, tot[0].s, tot[0].q, 0.0, tot[K - 1].m, tot[K - 1].s, tot[K - 1].q, 0.0};
+    if (a.mail_local == nullptr) {          // host-driven exchange: NCCL all-gather of local_stats
+        if (threadIdx.x == 0)
+            for (int i = 0; i < 8; i++) a.local_stats[i] = v[i];
+        return;
+    }
+    // fused exchange: the step kernel's last CTA stores this shard's statistics straight into every
+    // peer's mailbox over NVLink (one lane per peer), fences, then raises the epoch flag; k_finish
+    // on each rank waits for `world` flags.  No host call, no collective launch on the step.
+    const long long t = a.st->t;
+    if ((int)threadIdx.x < a.world) {
+        double *slot = a.mail_peer[threadIdx.x] + ((size_t)(t & 1) * a.world + a.rank) * 16;
+        for (int i = 0; i < 8; i++) slot[i] = v[i];
+        __threadfence_system();
+        *reinterpret_cast<volatile double *>(slot + 8) = (double)(t + 1);
     }
 }
 
@@ -597,14 +612,27 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
 template <bool APF>
 __global__ void __launch_bounds__(kBlock) k_finish(FilterArgs a) {
     __shared__ Lse3 s_tot[4];
+    const double *gath = a.gathered;
+    if (a.mail_local != nullptr) {          // peer-memory exchange: wait for every sender's epoch
+        const long long t = a.st->t;
+        const double *box = a.mail_local + (size_t)(t & 1) * a.world * 16;
+        if ((int)threadIdx.x < a.world) {
+            const volatile double *flag = box + (size_t)threadIdx.x * 16 + 8;
+            while (*flag != (double)(t + 1)) { }
+            __threadfence_system();
+        }
+        __syncthreads();
+        gath = box;                         // stride 16 doubles per sender
+    }
+    const int gstride = (a.mail_local != nullptr) ? 16 : 8;
     if (threadIdx.x == 0) {
         Lse3 w = lse3_empty(), x = lse3_empty();
         for (int r = 0; r < a.world; r++) {
-            const double *g = a.gathered + (size_t)r * 8;
+            const volatile double *g = gath + (size_t)r * gstride;
             w = lse3_merge(w, Lse3{g[0], g[1], g[2]});
             x = lse3_merge(x, Lse3{g[4], g[5], g[6]});
         }
-        const double *me = a.gathered + (size_t)a.rank * 8;
+        const volatile double *me = gath + (size_t)a.rank * gstride;
         s_tot[0] = w; s_tot[1] = x;
         s_tot[2] = Lse3{me[0], me[1], me[2]};
         s_tot[3] = Lse3{me[4], me[5], me[6]};
@@ -826,8 +854,16 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
         a.rank = d->world > 1 ? d->rank : 0;
         a.local_stats = d->local_stats;
         a.gathered = d->gathered;
-        SMCB_REQUIRE(a.world == 1 || (d->local_stats && d->gathered && a.rank >= 0 && a.rank < a.world),
-                     "smcb_filter_create: world > 1 needs local_stats / gathered buffers and a valid rank");
+        a.mail_local = (a.world > 1) ? d->mail_local : nullptr;
+        for (int r = 0; r < 8; r++) a.mail_peer[r] = (a.world > 1 && r < a.world) ? d->mail_peer[r] : nullptr;
+        SMCB_REQUIRE(a.world == 1 || (a.rank >= 0 && a.rank < a.world), "smcb_filter_create: bad rank");
+        SMCB_REQUIRE(a.world == 1 || a.mail_local || (d->local_stats && d->gathered),
+                     "smcb_filter_create: world > 1 needs either a peer mailbox or local_stats / gathered");
+        if (a.mail_local) {
+            SMCB_REQUIRE(a.world <= 8, "smcb_filter_create: the peer mailbox supports at most 8 ranks");
+            for (int r = 0; r < a.world; r++)
+                SMCB_REQUIRE(a.mail_peer[r] != nullptr, "smcb_filter_create: mail_peer[%d] is NULL", r);
+        }
     }
     {
         int64_t t2 = scan_tiles(n + 1);
@@ -863,7 +899,8 @@ extern "C" int smcb_filter_step_finish(smcb_filter *f) {
 
 extern "C" int smcb_filter_step(smcb_filter *f, int64_t nsteps) {
     SMCB_REQUIRE(f != nullptr, "smcb_filter_step: NULL filter");
-    SMCB_REQUIRE(f->args.world == 1, "smcb_filter_step: sharded filters use step_local / step_finish");
+    SMCB_REQUIRE(f->args.world == 1 || f->args.mail_local != nullptr,
+                 "smcb_filter_step: sharded filters without a peer mailbox use step_local / step_finish");
     // host mirror of t: the device advances by exactly one per launched step
     for (int64_t i = 0; i < nsteps; i++) {
         if (f->t_host >= f->desc.T) {
@@ -872,6 +909,7 @@ extern "C" int smcb_filter_step(smcb_filter *f, int64_t nsteps) {
         }
         int rc = (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
         if (rc) return rc;
+        if (f->args.world > 1 && (rc = f->launch_finish(f))) return rc;   // exchange happens on device
         f->t_host++;
     }
     return SMCB_OK;
@@ -933,5 +971,39 @@ extern "C" int smcb_filter_state(smcb_filter *f, double *out8) {
     SMCB_CUDA(cudaStreamSynchronize(f->ctx->stream));
     out8[0] = (double)h.t; out8[1] = (double)h.cur; out8[2] = (double)h.last_rs; out8[3] = h.logLt;
     out8[4] = h.ess; out8[5] = h.log_mean_w; out8[6] = h.wm; out8[7] = h.ws;
+    return SMCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// peer memory for the fused statistics exchange (one process per GPU, same node)
+// ---------------------------------------------------------------------------
+extern "C" int smcb_p2p_alloc(smcb_ctx *c, int64_t bytes, void **dev_ptr, unsigned char *handle64) {
+    SMCB_REQUIRE(c && dev_ptr && handle64 && bytes > 0, "smcb_p2p_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    SMCB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    SMCB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    SMCB_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_p2p_open(smcb_ctx *c, const unsigned char *handle64, void **dev_ptr) {
+    SMCB_REQUIRE(c && dev_ptr && handle64, "smcb_p2p_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SMCB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_p2p_close(void *peer_ptr) {
+    if (peer_ptr) SMCB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_p2p_free(void *dev_ptr) {
+    if (dev_ptr) SMCB_CUDA(cudaFree(dev_ptr));
     return SMCB_OK;
 }

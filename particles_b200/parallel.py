@@ -26,12 +26,18 @@ class ShardedFilter(_FusedEngine):
     in total; Philox counters are offset by the global particle index, so the union of the
     shards draws the same numbers as one big filter would."""
 
-    def __init__(self, spec, n_local, scheme, ESSrmin, seed, rank, world, group=None, noise=None):
+    def __init__(self, spec, n_local, scheme, ESSrmin, seed, rank, world, group=None, noise=None,
+                 exchange="p2p"):
+        """``exchange``: "p2p" (default, <= 8 ranks of one node) -- the kernels exchange the
+        statistics themselves through NVLink peer memory, the step loop runs without the host;
+        "nccl" -- one ``all_gather_into_tensor`` per step issued from Python."""
         if n_local % 2:
             raise ValueError("sharded filters need an even number of particles per rank")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         super().__init__(spec, n_local, scheme, ESSrmin, seed, noise=noise,
                          n_global=n_local * world, index_offset=rank * n_local,
-                         world=world, rank=rank, group=group)
+                         world=world, rank=rank, group=group, p2p=(exchange == "p2p" and world <= 8))
 
 
 class ShardedSMC:
@@ -39,7 +45,8 @@ class ShardedSMC:
     ``torch.distributed`` NCCL group): ``ShardedSMC(fk=..., N=<particles on THIS rank>).run()``.
     ``N_global = world * N``.  Stock (fused) models only."""
 
-    def __init__(self, fk=None, N=100, resampling="systematic", ESSrmin=0.5, seed=0, group=None):
+    def __init__(self, fk=None, N=100, resampling="systematic", ESSrmin=0.5, seed=0, group=None,
+                 exchange="p2p"):
         import time
         import torch.distributed as dist
         from .state_space_models import fused_spec
@@ -49,7 +56,8 @@ class ShardedSMC:
         self.fk, self.N = fk, N
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self._time = time
-        self._engine = ShardedFilter(spec, N, resampling, ESSrmin, seed, self.rank, self.world, group)
+        self._engine = ShardedFilter(spec, N, resampling, ESSrmin, seed, self.rank, self.world, group,
+                                     exchange=exchange)
         self.t, self.logLt, self.cpu_time = 0, 0.0, None
         self.ESSs, self.logLts, self.rs_flags = [], [], []
 

@@ -25,6 +25,13 @@ def main():
     T, n_local = 1000, 50_000
     fk = ssm.Bootstrap(ssm=ssm.StochVol(), data=[np.atleast_1d(v) for v in y[:T]])
     lls = []
+    per_mode = {}
+    for mode in ("nccl", "p2p"):       # same seed through both exchanges -> identical bits
+        f = ShardedFilter(ssm.fused_spec(fk), n_local, "systematic", 0.5, 123, rank, world, exchange=mode)
+        f.step(T)
+        per_mode[mode] = f.summ.clone()
+        f.close()
+    assert torch.equal(per_mode["nccl"], per_mode["p2p"]), "P2P and NCCL exchanges disagree"
     for seed in range(3):
         f = ShardedFilter(ssm.fused_spec(fk), n_local, "systematic", 0.5, seed, rank, world)
         f.step(T)
