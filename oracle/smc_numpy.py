@@ -210,6 +210,25 @@ class Normal:
         return normal_logpdf(x, self.loc, self.scale)
 
 
+class Poisson:
+    """particles/distributions.py:519-532; logpmf as scipy.stats.poisson evaluates it:
+    xlogy(k, mu) - gammaln(k + 1) - mu."""
+    dim = 1
+
+    def __init__(self, rate=1.0):
+        self.rate = rate
+
+    def rvs(self, size, z=None):
+        return np.random.poisson(self.rate, size=size)
+
+    def logpdf(self, x):
+        k = np.asarray(x, dtype=np.float64)
+        lg = np.vectorize(math.lgamma)(k + 1.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xl = np.where(k == 0, 0.0, k * np.log(self.rate))
+        return xl - lg - self.rate
+
+
 class Dirac:
     """particles/distributions.py:454-472."""
     dim = 1
@@ -356,6 +375,33 @@ class StochVol(SSM):
         xhatmmu = xhat - self.mu
         return 0.5 / self.sigma ** 2 * (xhatmmu ** 2 - xstmmu ** 2) - 0.5 * data[
             t + 1] ** 2 * np.exp(-xst) * (1.0 + xstmmu)
+
+
+class StochVolLeverage(StochVol):
+    """particles/state_space_models.py:501-543."""
+    default_params = {"mu": -1.02, "rho": 0.9702, "sigma": 0.178, "phi": 0.0}
+
+    def PY(self, t, xp, x):
+        if t == 0:
+            u = (x - self.mu) / self.sig0()
+        else:
+            u = (x - self.EXt(xp)) / self.sigma
+        std_x = np.exp(0.5 * x)
+        return Normal(loc=std_x * self.phi * u, scale=std_x * np.sqrt(1.0 - self.phi ** 2))
+
+
+class DiscreteCox(SSM):
+    """particles/state_space_models.py:611-630."""
+    default_params = {"mu": 0.0, "sigma": 1.0, "phi": 0.95}
+
+    def PX0(self):
+        return Normal(loc=self.mu, scale=self.sigma / np.sqrt(1.0 - self.phi ** 2))
+
+    def PX(self, t, xp):
+        return Normal(loc=self.mu + self.phi * (xp - self.mu), scale=self.sigma)
+
+    def PY(self, t, xp, x):
+        return Poisson(rate=np.exp(x))
 
 
 class LinearGauss(SSM):

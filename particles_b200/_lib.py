@@ -15,7 +15,7 @@ SUMMARY_STRIDE = 4
 RS_CODES = {"multinomial": 0, "stratified": 1, "systematic": 2, "residual": 3}
 FK_BOOTSTRAP, FK_GUIDED, FK_APF, FK_AUXBOOT = 0, 1, 2, 3
 MODEL_STOCHVOL, MODEL_LINGAUSS, MODEL_GORDON, MODEL_THETALOGISTIC = 0, 1, 2, 3
-MODEL_BEARINGS, MODEL_MVLINGAUSS = 4, 5
+MODEL_BEARINGS, MODEL_MVLINGAUSS, MODEL_DISCRETECOX, MODEL_STOCHVOLLEV = 4, 5, 6, 7
 LSE_SUM, LSE_MEAN, LSE_ESSL = 0, 1, 2
 
 c_dp = C.c_void_p  # device pointers travel as integers

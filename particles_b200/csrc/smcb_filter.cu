@@ -783,6 +783,8 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
         case SMCB_MODEL_LINGAUSS: rc = bind_fk<LinGaussM>(f); break;
         case SMCB_MODEL_GORDON: rc = bind_fk<GordonM>(f); break;
         case SMCB_MODEL_THETALOGISTIC: rc = bind_fk<ThetaLogisticM>(f); break;
+        case SMCB_MODEL_DISCRETECOX: rc = bind_fk<DiscreteCoxM>(f); break;
+        case SMCB_MODEL_STOCHVOLLEV: rc = bind_fk<StochVolLevM>(f); break;
         case SMCB_MODEL_BEARINGS: rc = bind_fk<BearingsM>(f); break;
         case SMCB_MODEL_MVLINGAUSS:
             if (d->dim == 2) rc = bind_fk<MvLinGaussM<2>>(f);

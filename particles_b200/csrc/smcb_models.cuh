@@ -170,6 +170,67 @@ struct ThetaLogisticM {
 };
 
 // ---------------------------------------------------------------------------
+// StochVolLeverage -- particles/state_space_models.py:501-543 (Bootstrap; the reference warns
+// that the inherited proposal / logeta are not valid for this model)
+// params: StochVol's 0..6, then 7 phi, 8 sqrt(1 - phi^2), 9 log sqrt(1 - phi^2)
+// ---------------------------------------------------------------------------
+struct StochVolLevM {
+    static constexpr int D = 1, NZ = 1;
+    static constexpr bool has_proposal = false;
+    double mu, rho, sigma, sig0, c0, lsigma, lsig0, phi, sq, lsq;
+    __host__ void load(const double *p) {
+        mu = p[0]; rho = p[1]; sigma = p[2]; sig0 = p[3]; c0 = p[4]; lsigma = p[5]; lsig0 = p[6];
+        phi = p[7]; sq = p[8]; lsq = p[9];
+    }
+    __device__ __forceinline__ void init(double &loc, double &scale, double &ls) const {
+        loc = mu; scale = sig0; ls = lsig0;
+    }
+    __device__ __forceinline__ void trans(const StepK &, double xp, double &loc, double &scale,
+                                          double &ls) const {
+        loc = c0 + rho * xp; scale = sigma; ls = lsigma;
+    }
+    // PY = Normal(s phi u, s sqrt(1 - phi^2)), s = exp(x/2), u = innovation of X_t (:533-543)
+    __device__ __forceinline__ double obs_logpdf(const StepK &k, double xp, double x) const {
+        const double u = (k.t == 0) ? (x - mu) / sig0 : (x - (c0 + rho * xp)) / sigma;
+        const double s = fexp(0.5 * x);
+        const double z = (k.y - s * phi * u) / (s * sq);
+        return -z * z / 2.0 - kHalfLog2Pi - (0.5 * x + lsq);     // log(s * sq) = x/2 + log sq
+    }
+    __device__ __forceinline__ void prop0(const StepK &, double &, double &, double &) const {}
+    __device__ __forceinline__ void prop(const StepK &, double, double &, double &, double &) const {}
+    __device__ __forceinline__ double logeta(const StepK &, double) const { return 0.0; }
+};
+
+// ---------------------------------------------------------------------------
+// DiscreteCox -- particles/state_space_models.py:611-630: Y_t | X_t ~ Poisson(exp(X_t))
+// params: 0 mu, 1 sigma, 2 phi, 3 sig0, 4 log sigma, 5 log sig0;
+// step constant sc0 = gammaln(y_t + 1) (host, scipy's term of poisson.logpmf)
+// ---------------------------------------------------------------------------
+struct DiscreteCoxM {
+    static constexpr int D = 1, NZ = 1;
+    static constexpr bool has_proposal = false;
+    double mu, sigma, phi, sig0, lsigma, lsig0;
+    __host__ void load(const double *p) {
+        mu = p[0]; sigma = p[1]; phi = p[2]; sig0 = p[3]; lsigma = p[4]; lsig0 = p[5];
+    }
+    __device__ __forceinline__ void init(double &loc, double &scale, double &ls) const {
+        loc = mu; scale = sig0; ls = lsig0;                         // :622-625
+    }
+    __device__ __forceinline__ void trans(const StepK &, double xp, double &loc, double &scale,
+                                          double &ls) const {
+        loc = mu + phi * (xp - mu); scale = sigma; ls = lsigma;     // :627-628
+    }
+    // Poisson(rate = e^x).logpmf(y) = xlogy(y, rate) - gammaln(y + 1) - rate, log(rate) = x
+    __device__ __forceinline__ double obs_logpdf(const StepK &k, double, double x) const {
+        const double xl = (k.y == 0.0) ? 0.0 : k.y * x;
+        return xl - k.sc0 - fexp(x);
+    }
+    __device__ __forceinline__ void prop0(const StepK &, double &, double &, double &) const {}
+    __device__ __forceinline__ void prop(const StepK &, double, double &, double &, double &) const {}
+    __device__ __forceinline__ double logeta(const StepK &, double) const { return 0.0; }
+};
+
+// ---------------------------------------------------------------------------
 // Feynman-Kac adaptors -- particles/state_space_models.py:299-438
 // ---------------------------------------------------------------------------
 template <int FK> struct FkTraits {

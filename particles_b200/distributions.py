@@ -87,6 +87,28 @@ class Normal(LocScaleDist):
         return out
 
 
+class Poisson(ProbDist):
+    """Poisson(rate) -- particles/distributions.py:519-532 (logpdf on the device; ``rate`` a CUDA
+    tensor or scalar, ``x`` the observed count).  scipy evaluates xlogy(k, mu) - gammaln(k+1) - mu."""
+    dtype = np.int64
+
+    def __init__(self, rate=1.0):
+        self.rate = rate
+
+    def rvs(self, size=None):
+        r = as_device(self.rate) if isinstance(self.rate, (torch.Tensor, np.ndarray)) else \
+            torch.full((1 if size is None else size,), float(self.rate), dtype=torch.float64, device="cuda")
+        return torch.poisson(r)
+
+    def logpdf(self, x):
+        from scipy.special import gammaln
+        k = float(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x).reshape(-1)[0])
+        rate = as_device(self.rate) if isinstance(self.rate, (torch.Tensor, np.ndarray)) else \
+            torch.full((1,), float(self.rate), dtype=torch.float64, device="cuda")
+        xl = 0.0 if k == 0 else k * torch.log(rate)
+        return xl - float(gammaln(k + 1.0)) - rate
+
+
 class Dirac(ProbDist):
     """Dirac mass -- particles/distributions.py:454-472."""
 

@@ -161,6 +161,33 @@ class StochVol(StateSpaceModel):
                 - 0.5 * y ** 2 * torch.exp(-xst) * (1.0 + xstmmu))
 
 
+class StochVolLeverage(StochVol):
+    """state_space_models.py:501-543."""
+    default_params = {"mu": -1.02, "rho": 0.9702, "sigma": 0.178, "phi": 0.0}
+
+    def PY(self, t, xp, x):
+        if t == 0:
+            u = (x - self.mu) / self.sig0()
+        else:
+            u = (x - self.EXt(xp)) / self.sigma
+        std_x = torch.exp(0.5 * x)
+        return dists.Normal(loc=std_x * self.phi * u, scale=std_x * np.sqrt(1.0 - self.phi ** 2))
+
+
+class DiscreteCox(StateSpaceModel):
+    """state_space_models.py:611-630."""
+    default_params = {"mu": 0.0, "sigma": 1.0, "phi": 0.95}
+
+    def PX0(self):
+        return dists.Normal(loc=self.mu, scale=self.sigma / np.sqrt(1.0 - self.phi ** 2))
+
+    def PX(self, t, xp):
+        return dists.Normal(loc=self.mu + self.phi * (xp - self.mu), scale=self.sigma)
+
+    def PY(self, t, xp, x):
+        return dists.Poisson(rate=torch.exp(x))
+
+
 class Gordon_etal(StateSpaceModel):
     """state_space_models.py:546-577."""
     default_params = {"a": 0.05, "b": 0.5, "c": 25.0, "d": 8.0, "e": 1.2, "sigmaX": 3.162278}
@@ -258,6 +285,22 @@ def spec_thetalogistic(m, T):
     return {"model": _lib.MODEL_THETALOGISTIC, "params": p, "dim": 1, "proposal": False}
 
 
+def spec_stochvollev(m, T):
+    sp = spec_stochvol(m, T)
+    sq = np.sqrt(1.0 - m.phi ** 2)
+    sp.update(model=_lib.MODEL_STOCHVOLLEV, params=sp["params"] + [m.phi, sq, np.log(sq)], proposal=False)
+    return sp
+
+
+def spec_discretecox(m, T, data=None):
+    from scipy.special import gammaln
+    sig0 = m.sigma / np.sqrt(1.0 - m.phi ** 2)
+    p = [m.mu, m.sigma, m.phi, sig0, np.log(m.sigma), np.log(sig0)]
+    y = _flat_data(data, 1).reshape(-1)
+    return {"model": _lib.MODEL_DISCRETECOX, "params": p, "dim": 1, "proposal": False,
+            "step_consts": gammaln(y + 1.0)}
+
+
 def spec_bearings(m, T):
     x0 = np.asarray(m.x0, dtype=np.float64).reshape(4)
     p = [m.sigmaX, m.sigmaY, np.log(m.sigmaY)] + list(x0)
@@ -307,7 +350,8 @@ def spec_mvlingauss(m, T, data=None):
 
 _SPECS = {"StochVol": spec_stochvol, "LinearGauss": spec_lingauss, "Gordon_etal": spec_gordon,
           "ThetaLogistic": spec_thetalogistic, "BearingsOnly": spec_bearings,
-          "MVLinearGauss": spec_mvlingauss, "MVLinearGauss_Guarniero_etal": spec_mvlingauss}
+          "MVLinearGauss": spec_mvlingauss, "MVLinearGauss_Guarniero_etal": spec_mvlingauss,
+          "StochVolLeverage": spec_stochvollev, "DiscreteCox": spec_discretecox}
 
 
 def fused_spec(fk):
@@ -325,7 +369,7 @@ def fused_spec(fk):
     make = _SPECS.get(type(ssm).__name__)
     if make is None:
         return None
-    spec = make(ssm, fk.T, fk.data) if make is spec_mvlingauss else make(ssm, fk.T)
+    spec = make(ssm, fk.T, fk.data) if make in (spec_mvlingauss, spec_discretecox) else make(ssm, fk.T)
     if spec is None:
         return None
     if kind != _lib.FK_BOOTSTRAP and not spec["proposal"]:

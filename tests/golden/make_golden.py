@@ -214,6 +214,17 @@ def gen_runs(g):
     _, ytl = tl.simulate(50)
     g["data/thetalogistic_seed4_T50"] = flat(ytl)
     run_case(g, "thetalogistic_boot", ssm.Bootstrap(ssm=tl, data=ytl), 1500, "residual", 0.5, 50)
+    # discrete Cox (Poisson observations) and stochastic volatility with leverage
+    np.random.seed(6)
+    dc = ssm.DiscreteCox(mu=0.5, sigma=0.5, phi=0.9)
+    _, yc = dc.simulate(60)
+    g["data/cox_seed6_T60"] = flat(yc).astype(np.float64)
+    run_case(g, "cox_boot", ssm.Bootstrap(ssm=dc, data=yc), 1500, "systematic", 0.5, 55)
+    np.random.seed(7)
+    svl = ssm.StochVolLeverage(phi=-0.6)
+    _, yv = svl.simulate(60)
+    g["data/svlev_seed7_T60"] = flat(yv)
+    run_case(g, "svlev_boot", ssm.Bootstrap(ssm=svl, data=yv), 1500, "stratified", 0.5, 56)
     # bearings-only, 4-D IndepProd state (C3 (i))
     np.random.seed(0)
     bo = ssm.BearingsOnly()

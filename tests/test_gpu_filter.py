@@ -46,6 +46,9 @@ def models():
                orc.LinearGauss(sigmaX=1.0, sigmaY=0.2, rho=0.9), "data/lg_seed2_T100", 100),
         "gordon": (ssm.Gordon_etal(), orc.Gordon_etal(), "data/gordon_seed3_T50", 50),
         "thetalog": (ssm.ThetaLogistic(), orc.ThetaLogistic(), "data/thetalogistic_seed4_T50", 50),
+        "cox": (ssm.DiscreteCox(mu=0.5, sigma=0.5, phi=0.9), orc.DiscreteCox(mu=0.5, sigma=0.5, phi=0.9),
+                "data/cox_seed6_T60", 60),
+        "svlev": (ssm.StochVolLeverage(phi=-0.6), orc.StochVolLeverage(phi=-0.6), "data/svlev_seed7_T60", 60),
     }
 
 
@@ -59,7 +62,8 @@ CASES = [
     ("sv", "apf", "systematic", 0.7), ("sv", "auxboot", "stratified", 0.5),
     ("lg", "boot", "stratified", 0.5), ("lg", "guided", "stratified", 0.5),
     ("lg", "apf", "systematic", 0.5), ("gordon", "boot", "systematic", 0.5),
-    ("thetalog", "boot", "stratified", 0.5),
+    ("thetalog", "boot", "stratified", 0.5), ("cox", "boot", "systematic", 0.5),
+    ("svlev", "boot", "stratified", 0.5),
 ]
 
 
