@@ -123,6 +123,26 @@ int smcb_mvnormal_logpdf(smcb_ctx *ctx, const double *x, const double *loc,
 int smcb_standard_normal(smcb_ctx *ctx, double *out, int64_t n);
 int smcb_uniform(smcb_ctx *ctx, double *out, int64_t n);
 
+/* ---------------------------------------------------------------------------
+ * SMC samplers: tempering / waste-free move step  (particles/smc_samplers.py)
+ * theta is (n, d) row-major, d <= 32
+ * ------------------------------------------------------------------------- */
+/* Tempering.current_target, smc_samplers.py:836-845, for the logistic-regression static model
+ * (book/smc_samplers/logistic_reg.py:60-67): prior MvNormal(0, prior_scale^2 I_d);
+ * llik = sum_t -log(1 + exp(-theta . data[t])) (StaticModel.loglik, 263-284); lpost = lprior + epn*llik */
+int smcb_logistic_target(smcb_ctx *ctx, const double *theta, int64_t n, int d, const double *data,
+                         int64_t n_data, double prior_scale, double epn, double *lprior,
+                         double *llik, double *lpost);
+/* ArrayRandomWalk.proposal, smc_samplers.py:624-629: prop = theta + z @ L.T; L_dev = device (d, d)
+ * row-major lower factor; z_in = injected N(0,1) (n, d) or NULL */
+int smcb_rw_propose(smcb_ctx *ctx, const double *theta, int64_t n, int d, const double *L_dev,
+                    const double *z_in, double *prop);
+/* ArrayMetropolis.step, smc_samplers.py:601-611: accept where u < exp(min(lpost' - lpost, 0)) and
+ * copy the proposal's fields in place; mean_acc (device scalar) = mean acceptance probability */
+int smcb_mh_accept(smcb_ctx *ctx, int64_t n, int d, double *theta, double *lprior, double *llik,
+                   double *lpost, const double *theta_p, const double *lprior_p, const double *llik_p,
+                   const double *lpost_p, const double *u_in, double *mean_acc);
+
 /* test hook: the step kernel's own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
  * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1) */
 int smcb_device_math(smcb_ctx *ctx, int fn, const double *x, double *out, int64_t n);

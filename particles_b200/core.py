@@ -359,6 +359,8 @@ class SMC:
             p["aux"] = p["wgts"]
 
     def _gather(self, X, A):
+        if not isinstance(X, (torch.Tensor, np.ndarray)):
+            return X[A]          # particle containers (smc_samplers.ThetaParticles) index themselves
         ctx = context()
         X = as_device(X)
         d = 1 if X.ndim == 1 else X.shape[1]

@@ -1,0 +1,240 @@
+// smcb_sampler.cu -- kernels of the tempering / waste-free SMC sampler move step
+// (particles/smc_samplers.py:596-629, 669-683, 797-936; BASELINE config 5):
+//   * tempered target of the Bayesian logistic regression: log prior, log-likelihood
+//     sum_t -log(1 + exp(-theta . x_t)) and log posterior for N parameter vectors at once
+//     (StaticModel.loglik loops over the data rows in Python, smc_samplers.py:263-284);
+//   * Gaussian random-walk proposal theta + z @ L.T (ArrayRandomWalk.proposal, 624-629);
+//   * Metropolis accept / copy-where (ArrayMetropolis.step, 601-611).
+// The log-likelihood is the only dense contraction on the path ((N x d) . (d x n_data) followed by a
+// softplus row-reduce).  It stays fp64 on the CUDA cores: the contraction is 2d = 40 flops per
+// (particle, datum) against ~50 fp64 instructions of softplus, so tensor cores would not move the
+// bound, and lower precision would change results.
+#include "smcb_common.cuh"
+#include "smcb_math.cuh"
+
+using namespace smcb;
+
+#define LAUNCHK(ctx, kern, grid, block, smem, ...)                               \
+    do {                                                                         \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+        (ctx)->launches++;                                                       \
+        SMCB_CUDA(cudaGetLastError());                                           \
+    } while (0)
+
+namespace smcb {
+
+constexpr int kSampBlock = 128;
+constexpr int kRowsPerTile = 32;       // data rows staged in shared memory per pass
+
+// -log(1 + exp(-lin)) = -(max(v, 0) + log1p(exp(-|v|))), v = -lin   (np.logaddexp(0, v))
+__device__ __forceinline__ double neg_softplus_neg(double lin) {
+    const double v = -lin;
+    const double e = fexp_neg(-fabs(v));
+    return -(fmax(v, 0.0) + flog_pos(1.0 + e));
+}
+
+// theta: (n, d) row-major.  D = d rounded up to a supported size (extra coordinates are zero).
+// Each thread owns TWO parameter vectors, so every data value read from shared memory feeds two
+// FMAs.  The sum over data rows runs in row order, as the reference's Python loop does.
+template <int D>
+__global__ void __launch_bounds__(kSampBlock) k_logistic_target(
+    const double *__restrict__ theta, int64_t n, int d, const double *__restrict__ data, int64_t n_data,
+    double prior_scale, double prior_lognorm, double epn, double *__restrict__ lprior,
+    double *__restrict__ llik, double *__restrict__ lpost) {
+    __shared__ __align__(16) double s_x[kRowsPerTile * D];
+    const int64_t i0 = 2 * ((int64_t)blockIdx.x * kSampBlock + threadIdx.x);
+    const bool v0 = i0 < n, v1 = i0 + 1 < n;
+    double th0[D], th1[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        th0[j] = (v0 && j < d) ? theta[i0 * d + j] : 0.0;
+        th1[j] = (v1 && j < d) ? theta[(i0 + 1) * d + j] : 0.0;
+    }
+    double l0 = 0.0, l1 = 0.0;
+    for (int64_t r0 = 0; r0 < n_data; r0 += kRowsPerTile) {
+        const int rows = (int)((n_data - r0) < kRowsPerTile ? (n_data - r0) : kRowsPerTile);
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * D; e += kSampBlock) {
+            const int r = e / D, j = e - r * D;
+            s_x[e] = (j < d) ? data[(r0 + r) * d + j] : 0.0;
+        }
+        __syncthreads();
+        for (int r = 0; r < rows; r++) {
+            const double *x = s_x + r * D;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j += 2) {
+                const double2 xx = *reinterpret_cast<const double2 *>(x + j);
+                a0 = fma(th0[j], xx.x, a0); a1 = fma(th1[j], xx.x, a1);
+                a0 = fma(th0[j + 1], xx.y, a0); a1 = fma(th1[j + 1], xx.y, a1);
+            }
+            l0 += neg_softplus_neg(a0);
+            l1 += neg_softplus_neg(a1);
+        }
+    }
+    // prior: MvNormal(loc=0, scale=s, cov=I).logpdf (distributions.py:949-959)
+    double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const double z0 = th0[j] / prior_scale, z1 = th1[j] / prior_scale;
+        q0 += z0 * z0; q1 += z1 * z1;
+    }
+    if (l0 != l0) l0 = -CUDART_INF;        // np.nan_to_num(l, nan=-inf), smc_samplers.py:283
+    if (l1 != l1) l1 = -CUDART_INF;
+    if (v0) {
+        const double lp = -0.5 * q0 - prior_lognorm;
+        lprior[i0] = lp; llik[i0] = l0;
+        lpost[i0] = (epn > 0.0) ? lp + epn * l0 : lp;        // smc_samplers.py:840-843
+    }
+    if (v1) {
+        const double lp = -0.5 * q1 - prior_lognorm;
+        lprior[i0 + 1] = lp; llik[i0 + 1] = l1;
+        lpost[i0 + 1] = (epn > 0.0) ? lp + epn * l1 : lp;
+    }
+}
+
+// prop = theta + z @ L.T   (L lower-triangular, row-major in constant-like kernel argument space)
+struct RwParams { double L[32 * 32]; int d; };
+
+__global__ void __launch_bounds__(kSampBlock) k_rw_propose(const double *__restrict__ theta, int64_t n,
+                                                          const double *__restrict__ Ldev, int d,
+                                                          Philox key, uint64_t call,
+                                                          const double *__restrict__ z_in,
+                                                          double *__restrict__ prop) {
+    extern __shared__ double s_L[];
+    for (int e = threadIdx.x; e < d * d; e += kSampBlock) s_L[e] = Ldev[e];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kSampBlock + threadIdx.x;
+    if (i >= n) return;
+    double z[32];
+    for (int j = 0; j < d; j += 2) {
+        if (z_in) {
+            z[j] = z_in[i * d + j];
+            if (j + 1 < d) z[j + 1] = z_in[i * d + j + 1];
+        } else {
+            uint32_t r[4];
+            philox4x32_10k((uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)call,
+                           ((uint32_t)(call >> 32) << 16) | ((uint32_t)(j >> 1) << 8) | kPurposeApi, key, r);
+            double za, zb;
+            box_muller_fast(r, za, zb);
+            z[j] = za;
+            if (j + 1 < d) z[j + 1] = zb;
+        }
+    }
+    for (int a = 0; a < d; a++) {
+        double acc = 0.0;
+        for (int b = 0; b <= a; b++) acc += z[b] * s_L[a * d + b];
+        prop[i * d + a] = theta[i * d + a] + acc;
+    }
+}
+
+// ArrayMetropolis.step (smc_samplers.py:601-611): pb = exp(min(lpost' - lpost, 0)); accept where
+// u < pb; copy theta / lprior / llik / lpost of accepted proposals over the current state.
+// Block sums of pb go to partials; the last block averages them in a fixed order.
+__global__ void __launch_bounds__(kSampBlock) k_mh_accept(int64_t n, int d, double *theta, double *lprior,
+                                                         double *llik, double *lpost,
+                                                         const double *__restrict__ theta_p,
+                                                         const double *__restrict__ lprior_p,
+                                                         const double *__restrict__ llik_p,
+                                                         const double *__restrict__ lpost_p,
+                                                         Philox key, uint64_t call,
+                                                         const double *__restrict__ u_in, double *partials,
+                                                         unsigned int *ticket, double *mean_acc) {
+    __shared__ double s_red[kSampBlock / 32];
+    __shared__ bool s_last;
+    const int64_t i = (int64_t)blockIdx.x * kSampBlock + threadIdx.x;
+    double pb = 0.0;
+    if (i < n) {
+        const double lp_acc = lpost_p[i] - lpost[i] + 0.0;
+        pb = exp(fmin(lp_acc, 0.0));                       // np.exp(np.clip(lp_acc, None, 0.))
+        if (lp_acc != lp_acc) pb = CUDART_NAN;
+        double u;
+        if (u_in) u = u_in[i];
+        else {
+            double u1;
+            uniform_pair(key, (uint64_t)i, (uint32_t)call, ((uint32_t)(call >> 32) << 8) | kPurposeApi, u, u1);
+        }
+        if (u < pb) {
+            for (int j = 0; j < d; j++) theta[i * d + j] = theta_p[i * d + j];
+            lprior[i] = lprior_p[i]; llik[i] = llik_p[i]; lpost[i] = lpost_p[i];
+        }
+    }
+    double acc = pb;
+#pragma unroll
+    for (int mask = 16; mask > 0; mask >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, mask);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kSampBlock / 32; w++) t += s_red[w];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; b++) t += ((volatile double *)partials)[b];
+        mean_acc[0] = t / (double)n;
+    }
+}
+
+}  // namespace smcb
+
+template <int D>
+static int launch_target(smcb_ctx *c, const double *theta, int64_t n, int d, const double *data,
+                         int64_t n_data, double s, double lognorm, double epn, double *lprior, double *llik,
+                         double *lpost) {
+    const int64_t pairs = (n + 1) / 2;
+    const int grid = (int)((pairs + kSampBlock - 1) / kSampBlock);
+    LAUNCHK(c, k_logistic_target<D>, grid, kSampBlock, 0, theta, n, d, data, n_data, s, lognorm, epn, lprior,
+            llik, lpost);
+    return SMCB_OK;
+}
+
+// Tempering.current_target (smc_samplers.py:836-845) for the logistic-regression model with an
+// MvNormal(loc=0, scale=prior_scale, cov=I_d) prior: lprior, llik, lpost = lprior + epn * llik.
+extern "C" int smcb_logistic_target(smcb_ctx *c, const double *theta, int64_t n, int d, const double *data,
+                                    int64_t n_data, double prior_scale, double epn, double *lprior,
+                                    double *llik, double *lpost) {
+    SMCB_REQUIRE(c && theta && data && lprior && llik && lpost, "smcb_logistic_target: NULL argument");
+    SMCB_REQUIRE(n >= 1 && n_data >= 1 && d >= 1 && d <= 32, "smcb_logistic_target: need 1 <= d <= 32");
+    SMCB_REQUIRE(prior_scale > 0.0, "smcb_logistic_target: prior scale must be positive");
+    const double lognorm = (double)d * log(prior_scale) + 0.0 + (double)d * kHalfLog2Pi;
+    if (d <= 4) return launch_target<4>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    if (d <= 8) return launch_target<8>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    if (d <= 12) return launch_target<12>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    if (d <= 16) return launch_target<16>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    if (d <= 20) return launch_target<20>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    if (d <= 24) return launch_target<24>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+    return launch_target<32>(c, theta, n, d, data, n_data, prior_scale, lognorm, epn, lprior, llik, lpost);
+}
+
+// ArrayRandomWalk.proposal (smc_samplers.py:624-629); L: DEVICE (d, d) row-major lower factor
+extern "C" int smcb_rw_propose(smcb_ctx *c, const double *theta, int64_t n, int d, const double *L_dev,
+                               const double *z_in, double *prop) {
+    SMCB_REQUIRE(c && theta && L_dev && prop, "smcb_rw_propose: NULL argument");
+    SMCB_REQUIRE(n >= 1 && d >= 1 && d <= 32, "smcb_rw_propose: need 1 <= d <= 32");
+    const uint64_t call = z_in ? 0 : c->api_counter++;
+    const int grid = (int)((n + kSampBlock - 1) / kSampBlock);
+    LAUNCHK(c, k_rw_propose, grid, kSampBlock, (size_t)d * d * sizeof(double), theta, n, L_dev, d,
+            key_of(c->seed), call, z_in, prop);
+    return SMCB_OK;
+}
+
+// ArrayMetropolis.step accept / copyto (smc_samplers.py:605-611); mean_acc: device scalar
+extern "C" int smcb_mh_accept(smcb_ctx *c, int64_t n, int d, double *theta, double *lprior, double *llik,
+                              double *lpost, const double *theta_p, const double *lprior_p,
+                              const double *llik_p, const double *lpost_p, const double *u_in,
+                              double *mean_acc) {
+    SMCB_REQUIRE(c && theta && lprior && llik && lpost && theta_p && lprior_p && llik_p && lpost_p && mean_acc,
+                 "smcb_mh_accept: NULL argument");
+    SMCB_REQUIRE(n >= 1 && d >= 1, "smcb_mh_accept: bad sizes");
+    const int grid = (int)((n + kSampBlock - 1) / kSampBlock);
+    SMCB_REQUIRE((size_t)grid <= kWsPartials, "smcb_mh_accept: too many particles for the workspace");
+    const uint64_t call = u_in ? 0 : c->api_counter++;
+    LAUNCHK(c, k_mh_accept, grid, kSampBlock, 0, n, d, theta, lprior, llik, lpost, theta_p, lprior_p, llik_p,
+            lpost_p, key_of(c->seed), call, u_in, c->ws, c->counters + 2, mean_acc);
+    return SMCB_OK;
+}
