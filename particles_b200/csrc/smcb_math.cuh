@@ -79,6 +79,16 @@ __device__ __forceinline__ double fexp_neg(double x) {
     return (x < -708.0) ? 0.0 : res;
 }
 
+// exp(x) for |x| < 700 guaranteed by the caller's domain (no range selects at all); -inf -> NaN!
+__device__ __forceinline__ double fexp_mid(double x) {
+    const double t = fma(x, SMCB_LOG2E, kRintMagic);
+    const double kd = t - kRintMagic;
+    const int k = __double2loint(t);
+    double r = fma(kd, -SMCB_LN2_HI, x);
+    r = fma(kd, -SMCB_LN2_LO, r);
+    return horner(kExpC, r) * __hiloint2double((k + 1023) << 20, 0);
+}
+
 // log(x) for positive NORMAL x (the 53-bit uniforms of box_muller are >= 2^-54)
 __device__ __forceinline__ double flog_pos(double x) {
     int hi = __double2hiint(x), lo = __double2loint(x);
