@@ -143,6 +143,17 @@ int smcb_mh_accept(smcb_ctx *ctx, int64_t n, int d, double *theta, double *lprio
                    double *lpost, const double *theta_p, const double *lprior_p, const double *llik_p,
                    const double *lpost_p, const double *u_in, double *mean_acc);
 
+/* MCMCSequenceWF.__call__, smc_samplers.py:672-683, fused for the logistic model + random-walk
+ * Metropolis: ONE launch runs the P-1 Metropolis steps of all M chains.  Inputs: the M resampled
+ * particles; outputs: the P*M particles of the next generation in concatenate(xs) order and the
+ * (P-1, M) acceptance probabilities.  z_in (P-1, M, d) / u_in (P-1, M): injected noise or NULL. */
+int smcb_logistic_wf_move(smcb_ctx *ctx, int64_t M, int d, int P, const double *theta0,
+                          const double *lprior0, const double *llik0, const double *lpost0,
+                          const double *data, int64_t n_data, double prior_scale, double epn,
+                          const double *L_dev, const double *z_in, const double *u_in,
+                          double *theta_out, double *lprior_out, double *llik_out, double *lpost_out,
+                          double *pb_out);
+
 /* test hook: the step kernel's own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
  * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1) */
 int smcb_device_math(smcb_ctx *ctx, int fn, const double *x, double *out, int64_t n);

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "smcb_uniform": (C.c_int, [C.c_void_p, c_dp, C.c_int64]),
     "smcb_logistic_target": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int, c_dp, C.c_int64, C.c_double,
                                        C.c_double, c_dp, c_dp, c_dp]),
+    "smcb_logistic_wf_move": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                        C.c_int64, C.c_double, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                        c_dp, c_dp]),
     "smcb_rw_propose": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int, c_dp, c_dp, c_dp]),
     "smcb_mh_accept": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                  c_dp, c_dp]),

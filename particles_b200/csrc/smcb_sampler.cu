@@ -180,7 +180,177 @@ __global__ void __launch_bounds__(kSampBlock) k_mh_accept(int64_t n, int d, doub
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused waste-free move (MCMCSequenceWF.__call__, smc_samplers.py:672-683, with the
+// ArrayRandomWalk / ArrayMetropolis step of 601-629 and the tempered logistic target): every
+// chain is independent, so ONE launch runs all P-1 Metropolis steps of all M chains and writes
+// the (P*M) particles of the next generation in the reference's order (xs[0] | xs[1] | ...).
+// kWfLanes lanes of a warp share a chain: each takes every kWfLanes-th data row, a butterfly
+// reduction gives all of them the same log-likelihood bits, so they take the same decision.
+// The data matrix is staged in shared memory once per CTA when it fits (it is re-used P-1 times).
+// ---------------------------------------------------------------------------
+constexpr int kWfBlock = 512;
+constexpr int kWfLanes = 16;
+
+template <int D>
+__global__ void __launch_bounds__(kWfBlock) k_logistic_wf_move(
+    int64_t M, int d, int P, const double *__restrict__ theta0, const double *__restrict__ lprior0,
+    const double *__restrict__ llik0, const double *__restrict__ lpost0, const double *__restrict__ data,
+    int64_t n_data, int tile_rows, double prior_scale, double prior_lognorm, double epn,
+    const double *__restrict__ Ldev, Philox key, uint64_t call, const double *__restrict__ z_in,
+    const double *__restrict__ u_in, double *__restrict__ theta_out, double *__restrict__ lprior_out,
+    double *__restrict__ llik_out, double *__restrict__ lpost_out, double *__restrict__ pb_out) {
+    extern __shared__ __align__(16) double s_mem[];
+    double *s_L = s_mem;                 // D x D
+    double *s_x = s_mem + D * D;         // tile_rows x D
+    const int g = threadIdx.x % kWfLanes;
+    const int64_t c = (int64_t)blockIdx.x * (kWfBlock / kWfLanes) + threadIdx.x / kWfLanes;
+    const bool valid = c < M;
+    for (int e = threadIdx.x; e < D * D; e += kWfBlock) {
+        const int a = e / D, b = e - a * D;
+        s_L[e] = (a < d && b < d) ? Ldev[a * d + b] : 0.0;
+    }
+    const bool resident = tile_rows >= n_data;     // whole data set in shared memory
+    if (resident) {
+        for (int e = threadIdx.x; e < (int)n_data * D; e += kWfBlock) {
+            const int r = e / D, j = e - r * D;
+            s_x[e] = (j < d) ? data[(int64_t)r * d + j] : 0.0;
+        }
+    }
+    __syncthreads();
+    double th[D], lpr = 0.0, ll = 0.0, lp = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) th[j] = (valid && j < d) ? theta0[c * d + j] : 0.0;
+    if (valid) { lpr = lprior0[c]; ll = llik0[c]; lp = lpost0[c]; }
+    // generation row 0: the resampled particles themselves
+    if (valid) {
+        for (int j = g; j < d; j += kWfLanes) theta_out[c * d + j] = th[j];
+        if (g == 0) { lprior_out[c] = lpr; llik_out[c] = ll; lpost_out[c] = lp; }
+    }
+    for (int s = 1; s < P; s++) {
+        double z[D], pr[D];
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+            if (z_in) {
+                z[j] = (valid && j < d) ? z_in[((int64_t)(s - 1) * M + c) * d + j] : 0.0;
+                z[j + 1] = (valid && j + 1 < d) ? z_in[((int64_t)(s - 1) * M + c) * d + j + 1] : 0.0;
+            } else {
+                uint32_t r[4];
+                philox4x32_10k((uint32_t)c, (uint32_t)((uint64_t)c >> 32), (uint32_t)call,
+                               ((uint32_t)s << 16) | ((uint32_t)(j >> 1) << 8) | kPurposeNormal, key, r);
+                box_muller_fast(r, z[j], z[j + 1]);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b <= a; b++) acc += z[b] * s_L[a * D + b];
+            pr[a] = th[a] + acc;
+        }
+        double part = 0.0;
+        for (int64_t r0 = 0; r0 < n_data; r0 += tile_rows) {
+            const int rows = (int)((n_data - r0) < tile_rows ? (n_data - r0) : tile_rows);
+            if (!resident) {
+                __syncthreads();
+                for (int e = threadIdx.x; e < rows * D; e += kWfBlock) {
+                    const int r = e / D, j = e - r * D;
+                    s_x[e] = (j < d) ? data[(r0 + r) * d + j] : 0.0;
+                }
+                __syncthreads();
+            }
+            for (int r = g; r < rows; r += kWfLanes) {
+                const double *x = s_x + r * D;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; j += 2) {
+                    const double2 xx = *reinterpret_cast<const double2 *>(x + j);
+                    a0 = fma(pr[j], xx.x, a0);
+                    a1 = fma(pr[j + 1], xx.y, a1);
+                }
+                part += neg_softplus_neg(a0 + a1);
+            }
+        }
+#pragma unroll
+        for (int m = kWfLanes / 2; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+        double llp = (part != part) ? -CUDART_INF : part;
+        double q = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) { const double zz = pr[j] / prior_scale; q += zz * zz; }
+        const double lprp = -0.5 * q - prior_lognorm;
+        const double lpp = (epn > 0.0) ? lprp + epn * llp : lprp;
+        const double lp_acc = lpp - lp + 0.0;
+        double pb = exp(fmin(lp_acc, 0.0));
+        if (lp_acc != lp_acc) pb = CUDART_NAN;
+        double u;
+        if (u_in) u = valid ? u_in[(int64_t)(s - 1) * M + c] : 1.0;
+        else {
+            double u1;
+            uniform_pair(key, (uint64_t)c, (uint32_t)call, ((uint32_t)s << 16) | kPurposeUniform, u, u1);
+        }
+        if (u < pb) {
+#pragma unroll
+            for (int j = 0; j < D; j++) th[j] = pr[j];
+            lpr = lprp; ll = llp; lp = lpp;
+        }
+        if (valid) {
+            const int64_t row = (int64_t)s * M + c;
+            for (int j = g; j < d; j += kWfLanes) theta_out[row * d + j] = th[j];
+            if (g == 0) {
+                lprior_out[row] = lpr; llik_out[row] = ll; lpost_out[row] = lp;
+                pb_out[(int64_t)(s - 1) * M + c] = pb;
+            }
+        }
+    }
+}
+
 }  // namespace smcb
+
+template <int D>
+static int launch_wf(smcb_ctx *c, int64_t M, int d, int P, const double *theta0, const double *lprior0,
+                     const double *llik0, const double *lpost0, const double *data, int64_t n_data, double s,
+                     double lognorm, double epn, const double *L, const double *z_in, const double *u_in,
+                     double *theta_out, double *lprior_out, double *llik_out, double *lpost_out, double *pb_out) {
+    const size_t budget = 200 * 1024;                 // of the 227 KB a CTA may use
+    const size_t fixed = (size_t)D * D * sizeof(double);
+    int64_t tile_rows = (int64_t)((budget - fixed) / (D * sizeof(double)));
+    if (tile_rows > n_data) tile_rows = n_data;
+    const size_t smem = fixed + (size_t)tile_rows * D * sizeof(double);
+    SMCB_CUDA(cudaFuncSetAttribute(k_logistic_wf_move<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int chains_per_block = kWfBlock / kWfLanes;
+    const int grid = (int)((M + chains_per_block - 1) / chains_per_block);
+    const uint64_t call = (z_in && u_in) ? 0 : c->api_counter++;
+    LAUNCHK(c, k_logistic_wf_move<D>, grid, kWfBlock, smem, M, d, P, theta0, lprior0, llik0, lpost0, data, n_data,
+            (int)tile_rows, s, lognorm, epn, L, key_of(c->seed), call, z_in, u_in, theta_out, lprior_out, llik_out,
+            lpost_out, pb_out);
+    return SMCB_OK;
+}
+
+// MCMCSequenceWF.__call__ (smc_samplers.py:672-683) for the logistic model + random-walk Metropolis:
+// inputs = the M resampled particles (theta0 (M,d), lprior0, llik0, lpost0), outputs = the P*M
+// particles of the next generation in concatenate(xs) order, pb_out (P-1, M) acceptance probabilities.
+extern "C" int smcb_logistic_wf_move(smcb_ctx *c, int64_t M, int d, int P, const double *theta0,
+                                     const double *lprior0, const double *llik0, const double *lpost0,
+                                     const double *data, int64_t n_data, double prior_scale, double epn,
+                                     const double *L_dev, const double *z_in, const double *u_in,
+                                     double *theta_out, double *lprior_out, double *llik_out,
+                                     double *lpost_out, double *pb_out) {
+    SMCB_REQUIRE(c && theta0 && lprior0 && llik0 && lpost0 && data && L_dev && theta_out && lprior_out &&
+                     llik_out && lpost_out && pb_out, "smcb_logistic_wf_move: NULL argument");
+    SMCB_REQUIRE(M >= 1 && P >= 2 && n_data >= 1 && d >= 1 && d <= 32, "smcb_logistic_wf_move: bad sizes");
+    SMCB_REQUIRE(P < 65536, "smcb_logistic_wf_move: len_chain must be < 65536");
+    const double lognorm = (double)d * log(prior_scale) + 0.0 + (double)d * kHalfLog2Pi;
+#define WF(DD) return launch_wf<DD>(c, M, d, P, theta0, lprior0, llik0, lpost0, data, n_data, prior_scale, lognorm, \
+                                    epn, L_dev, z_in, u_in, theta_out, lprior_out, llik_out, lpost_out, pb_out)
+    if (d <= 4) WF(4);
+    if (d <= 8) WF(8);
+    if (d <= 12) WF(12);
+    if (d <= 16) WF(16);
+    if (d <= 20) WF(20);
+    if (d <= 24) WF(24);
+    WF(32);
+#undef WF
+}
 
 template <int D>
 static int launch_target(smcb_ctx *c, const double *theta, int64_t n, int d, const double *data,

@@ -87,6 +87,24 @@ class LogisticRegression:
         _lib.check(ctx.lib.smcb_standard_normal(ctx.handle, ptr(z), size * self.d))
         return (self.prior_scale * z).reshape(size, self.d)     # loc + scale * (z @ I)
 
+    def wf_move(self, x, epn, P, noise=None):
+        """Fused waste-free move (smcb_logistic_wf_move): x = the M resampled particles with their
+        lprior / llik / lpost at exponent ``epn`` and ``shared['chol_cov']``; returns P*M particles."""
+        ctx = context()
+        M, d = x.theta.shape
+        out = x.__class__(shared=x.shared.copy(), theta=empty((P * M, d)), lprior=empty(P * M),
+                          llik=empty(P * M), lpost=empty(P * M))
+        pb = empty((P - 1, M))
+        z = u = None
+        if noise is not None:
+            z, u = as_device(noise[0]), as_device(noise[1])
+        _lib.check(ctx.lib.smcb_logistic_wf_move(
+            ctx.handle, M, d, P, ptr(x.theta), ptr(x.lprior), ptr(x.llik), ptr(x.lpost), ptr(self.data), self.T,
+            self.prior_scale, float(epn), ptr(x.shared["chol_cov"]), ptr(z), ptr(u), ptr(out.theta),
+            ptr(out.lprior), ptr(out.llik), ptr(out.lpost), ptr(pb)))
+        out.shared["acc_rates"] = x.shared.get("acc_rates", []) + [pb.mean(dim=1)]
+        return out
+
     def target(self, x, epn):
         ctx = context()
         n = x.theta.shape[0]
@@ -139,7 +157,10 @@ class MCMCSequence:
 class MCMCSequenceWF(MCMCSequence):
     """Waste-free: keep every intermediate state, smc_samplers.py:669-683."""
 
-    def __call__(self, x, target):
+    def __call__(self, x, target, noise=None):
+        fused = getattr(target, "fused_wf", None)
+        if fused is not None and isinstance(self.mcmc, ArrayRandomWalk) and self.nsteps >= 1:
+            return fused(x, self.nsteps + 1, noise)     # all chains, all steps: one kernel launch
         xs, ars = [x], []
         for _ in range(self.nsteps):
             x = x.copy()
@@ -214,7 +235,11 @@ class Tempering(FKSMCsampler):
         return self.logG_tempering(x, self.deltas[t])
 
     def current_target(self, epn):
-        return lambda x: self.model.target(x, epn)
+        def func(x):
+            self.model.target(x, epn)
+        if hasattr(self.model, "wf_move"):      # lets MCMCSequenceWF run the whole move in one kernel
+            func.fused_wf = lambda x, P, noise=None: self.model.wf_move(x, epn, P, noise)
+        return func
 
     def _M0(self, N):
         x0 = ThetaParticles(theta=self.model.prior_rvs(N))

@@ -152,3 +152,45 @@ def test_fixed_tempering_and_standard_move():
                ESSrmin=1.0, seed=2)
     b.run()
     assert b.t == len(ladder) and abs(a.logLt - b.logLt) < 0.5
+
+
+@gpu
+def test_fused_wastefree_move_vs_oracle():
+    """The one-launch waste-free move (P-1 Metropolis steps of every chain) with injected noise against
+    the oracle's MCMCSequenceWF: same accept/reject path for (almost) every chain, same output order."""
+    torch = pytest.importorskip("torch")
+    from particles_b200 import smc_samplers as ssp
+    d, M, P = 5, 700, 9
+    data = sp.synthetic_logistic(180, d, seed=5)
+    r = np.random.RandomState(7)
+    theta = r.randn(M, d)
+    W = orc.exp_and_normalise(r.randn(M))
+    z, u = r.standard_normal((P - 1, M, d)), r.rand(P - 1, M)
+    m = sp.LogisticModel(data)
+    fk = sp.AdaptiveTemperingWF(m, len_chain=P)
+    xo = sp.ThetaParticles(theta=theta.copy())
+    fk.target(0.45)(xo)
+    fk.calibrate(W, xo)
+    xs, x = [xo], xo
+    for s in range(P - 1):                                  # MCMCSequenceWF with the injected draws
+        x = x.copy()
+        xprop = sp.ThetaParticles(theta=x.theta + z[s] @ x.shared["chol_cov"].T)
+        fk.target(0.45)(xprop)
+        pb = np.exp(np.clip(xprop.lpost - x.lpost, None, 0.0))
+        x.copyto(xprop, where=u[s] < pb)
+        xs.append(x)
+    ref = sp.ThetaParticles.concatenate(*xs)
+    mdev = ssp.LogisticRegression(data=data)
+    xd = ssp.ThetaParticles(theta=torch.from_numpy(theta).cuda())
+    mdev.target(xd, 0.45)
+    ssp.ArrayRandomWalk().calibrate(torch.from_numpy(W).cuda(), xd)
+    out = mdev.wf_move(xd, 0.45, P, noise=(z, u))
+    assert out.theta.shape == (P * M, d)
+    lp = host(out.lpost).reshape(P, M)
+    same_chain = np.all(np.isclose(lp, ref.lpost.reshape(P, M), rtol=1e-9), axis=0)
+    assert same_chain.mean() > 0.99                      # a draw within 1e-10 of its threshold may flip a chain
+    th = host(out.theta).reshape(P, M, d)
+    np.testing.assert_allclose(th[:, same_chain], ref.theta.reshape(P, M, d)[:, same_chain], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(host(out.llik).reshape(P, M)[:, same_chain], ref.llik.reshape(P, M)[:, same_chain],
+                               rtol=1e-11, atol=1e-10)
+    assert np.array_equal(th[0], theta)                  # generation row 0 = the resampled particles
