@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsmcb.so")
-SOURCES = ["smcb_api.cu", "smcb_filter.cu", "smcb_sampler.cu"]
+SOURCES = ["smcb_api.cu", "smcb_filter.cu", "smcb_filter_nd.cu", "smcb_sampler.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "--use_fast_math=false",
@@ -42,13 +42,17 @@ def build(force=False, verbose=False):
         return SO
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    objs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
-        objs.append(obj)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:      # translation units in parallel
+        objs = list(pool.map(compile_one, SOURCES))
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO]
                           + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     return SO
