@@ -249,7 +249,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    launches = eng.ctx.launches - launches0
+    launches = eng.ctx.launches - launches0      # kernels launched in the timed region (counted by libsmcb)
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     table = eng.summ.cpu().numpy()
     n_rs = int(table[:, 2].sum())

@@ -120,9 +120,12 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
         int64_t t2 = scan_tiles(n + 1);
         f->grid_scan2 = (int)(t2 < kMaxGrid ? t2 : kMaxGrid);
     }
-    // single-device filters run their step loop as one CUDA graph (SMCB_NO_GRAPH=1 disables it);
-    // if the driver refuses conditional nodes we silently keep the launch-per-step loop
-    if (a.world == 1 && getenv("SMCB_NO_GRAPH") == nullptr) {
+    // Optional: the whole step loop as ONE CUDA graph (WHILE + IF/ELSE conditional nodes, branch-
+    // specialised kernels).  Measured on this driver (profiles/graph_vs_loop.py) a conditional-node
+    // iteration costs ~7 us more than the two plain launches it replaces (14 -> 21 us per step at
+    // N = 1e3, 121 -> 130 us at N = 1e7), so the launch-per-step loop stays the default and the
+    // graph is opt-in (SMCB_GRAPH=1).
+    if (a.world == 1 && getenv("SMCB_GRAPH") != nullptr) {
         if (f->build_graph(f) != SMCB_OK) {
             cudaGetLastError();
             f->has_graph = false;
