@@ -25,5 +25,7 @@ done
 # a .ncu-rep with imported sources is ~32 MB and gpurun brings back at most 64 MiB:
 # keep the CSV exports of all three and the binary report of the dominant kernel only
 rm -f $OUT/scan_$TAG.ncu-rep $OUT/movers_$TAG.ncu-rep
+# ... and even that one only while it is small enough to travel (the embedded cubin grows with the library)
+find $OUT -name "*.ncu-rep" -size +30M -delete
 ls -la $OUT
 du -sh $OUT
