@@ -165,9 +165,9 @@ def run_reference(args):
         mem_workers = int(psutil.virtual_memory().available / 2.0e9)
     except Exception:
         mem_workers = 16
-    # replicas beyond ~32 saturate the host's memory bandwidth on this class of box (measured: 16
-    # workers 2.2e8, 128 workers 0.9e8 particle-steps/s in aggregate), so the arm is capped there
-    workers = max(1, min(cores, mem_workers, 32))
+    # replicas beyond ~16 saturate the host's memory bandwidth on this class of box (measured: 16
+    # workers 2.2e8, 32 workers 1.5e8, 128 workers 0.9e8 particle-steps/s in aggregate): capped at 16
+    workers = max(1, min(cores, mem_workers, 16))
     n = N_PER_GPU
     K = max(1, min(args.steps, 4))              # bounded sample: ~3 s per step per worker
     reps = max(1, min(args.warmup, 1))
