@@ -5,7 +5,8 @@
 
 #include "smcb_filter_kernels.cuh"
 
-int smcb_bind_nd(smcb_filter *f);   // smcb_filter_nd.cu
+int smcb_bind_nd(smcb_filter *f);      // smcb_filter_nd.cu
+int smcb_bind_1d_more(smcb_filter *f); // smcb_filter_1d.cu
 
 static int smcb_bind_1d(smcb_filter *f) {
     const smcb_filter_desc *d = &f->desc;
@@ -17,10 +18,10 @@ static int smcb_bind_1d(smcb_filter *f) {
 #else
         case SMCB_MODEL_STOCHVOL: return bind_fk<StochVolM>(f);
         case SMCB_MODEL_LINGAUSS: return bind_fk<LinGaussM>(f);
-        case SMCB_MODEL_GORDON: return bind_fk<GordonM>(f);
-        case SMCB_MODEL_THETALOGISTIC: return bind_fk<ThetaLogisticM>(f);
-        case SMCB_MODEL_DISCRETECOX: return bind_fk<DiscreteCoxM>(f);
-        case SMCB_MODEL_STOCHVOLLEV: return bind_fk<StochVolLevM>(f);
+        case SMCB_MODEL_GORDON:
+        case SMCB_MODEL_THETALOGISTIC:
+        case SMCB_MODEL_DISCRETECOX:
+        case SMCB_MODEL_STOCHVOLLEV: return smcb_bind_1d_more(f);
 #endif
         default:
             set_error("fused filter: model id %d is not available in the fused 1-D family", d->model);
@@ -225,15 +226,12 @@ extern "C" int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *ou
             SMCB_CUDA(cudaEventRecord(ev[2 * k + 1], s));
             kind[k++] = 0;
         } else {
-            int flag = 0;                              // profiling pass: read the branch, then launch
-            SMCB_CUDA(cudaMemcpyAsync(&flag, &f->st->rs_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-            SMCB_CUDA(cudaStreamSynchronize(s));
             f->timed_ev = ev + 2 * k;
             f->timed_kind = kind + k;
-            int rc = f->launch_step_spec(f, flag);
+            int rc = f->launch_step(f);
             f->timed_ev = nullptr;
             if (rc) return rc;
-            k += flag ? per : 1;
+            k += per;
         }
         f->t_host++;
     }

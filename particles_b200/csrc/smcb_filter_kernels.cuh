@@ -397,9 +397,9 @@ static __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 #ifndef SMCB_MINB
 #define SMCB_MINB 3
 #endif
-// MODE 0: both branches, chosen at run time from FilterDev.rs_flag (host-driven loops);
-// MODE 1: identity branch only, MODE 2: resampling branch only -- the two bodies of the IF node
-// of the CUDA graph, each with its own register allocation and shared-memory footprint.
+// MODE 0: both branches, chosen at run time from FilterDev.rs_flag.  MODE 1 / 2 compile the identity /
+// resampling branch alone (own register allocation); measured no faster than MODE 0 (DESIGN.md
+// section 6), so only MODE 0 is instantiated.
 template <class M, int FK, int SCHEME, int MODE = 0>
 __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
@@ -677,7 +677,6 @@ struct smcb_filter {
     int (*launch_init)(smcb_filter *);
     int (*launch_step)(smcb_filter *);
     int (*launch_finish)(smcb_filter *);
-    int (*launch_step_spec)(smcb_filter *, int rs);   // specialised kernels, branch known on the host
     int (*build_graph)(smcb_filter *);
     // one CUDA graph for the whole step loop: WHILE(t < t_stop) { k_cond; IF(rs) {scan; move} ELSE {move} }
     cudaGraph_t graph;
@@ -708,40 +707,6 @@ static int launch_step_t(smcb_filter *f) {
     before();
     k_move<M, FK, SCHEME><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
     after(3);
-    f->ctx->launches++;
-    SMCB_CUDA(cudaGetLastError());
-    return SMCB_OK;
-}
-
-// same step with the branch known on the host (profiling pass): specialised kernels, event pairs
-template <class M, int FK, int SCHEME>
-static int launch_step_spec_t(smcb_filter *f, int rs) {
-    M model;
-    model.load(f->desc.params);
-    cudaStream_t s = f->ctx->stream;
-    cudaEvent_t *ev = f->timed_ev;
-    int j = 0;
-    auto before = [&]() { if (ev) cudaEventRecord(ev[2 * j], s); };
-    auto after = [&](int kind) { if (ev) { cudaEventRecord(ev[2 * j + 1], s); f->timed_kind[j] = kind; j++; } };
-    if (rs) {
-        before();
-        k_scan_w<M, FK><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
-        after(1);
-        f->ctx->launches++;
-        if (SCHEME == SMCB_RS_MULTINOMIAL) {
-            before();
-            k_scan_spacings<<<f->grid_scan2, kBlock, 0, s>>>(f->args);
-            after(2);
-            f->ctx->launches++;
-        }
-        before();
-        k_move<M, FK, SCHEME, 2><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
-        after(3);
-    } else {
-        before();
-        k_move<M, FK, SMCB_RS_SYSTEMATIC, 1><<<f->grid_move, kBlock, 0, s>>>(model, f->args);
-        after(3);
-    }
     f->ctx->launches++;
     SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
@@ -802,13 +767,13 @@ static int build_graph_t(smcb_filter *f) {
             prev = cur;
         }
         cudaKernelNodeParams k3 = {};
-        k3.func = (void *)k_move<M, FK, SCHEME, 2>;
+        k3.func = (void *)k_move<M, FK, SCHEME, 0>;
         k3.gridDim = dim3(f->grid_move); k3.blockDim = dim3(kBlock); k3.kernelParams = ka2;
         SMCB_CUDA(cudaGraphAddKernelNode(&cur, g_rs, &prev, 1, &k3));
     }
     {   // ELSE body: the streaming step
         cudaKernelNodeParams k4 = {};
-        k4.func = (void *)k_move<M, FK, SMCB_RS_SYSTEMATIC, 1>;
+        k4.func = (void *)k_move<M, FK, SCHEME, 0>;
         k4.gridDim = dim3(f->grid_move); k4.blockDim = dim3(kBlock); k4.kernelParams = ka2;
         SMCB_CUDA(cudaGraphAddKernelNode(&cur, g_id, nullptr, 0, &k4));
     }
@@ -843,7 +808,6 @@ static int bind_one(smcb_filter *f) {
     f->launch_init = launch_init_t<M, FK>;
     f->launch_step = launch_step_t<M, FK, SCHEME>;
     f->launch_finish = launch_finish_t<FK>;
-    f->launch_step_spec = launch_step_spec_t<M, FK, SCHEME>;
     f->build_graph = build_graph_t<M, FK, SCHEME>;
     int nb = 0;
     SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_move<M, FK, SCHEME>, kBlock, 0));

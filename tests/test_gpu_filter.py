@@ -477,3 +477,43 @@ def test_history_and_moments_collectors(golden):
     assert sorted(part.hist.X) == [0, 10, 20]
     with pytest.raises(ValueError):
         mk(store_history=-2)
+
+
+@pytest.mark.parametrize("N,T,essrmin,scheme", [(1, 5, 0.5, "systematic"), (2, 7, 1.0, "stratified"),
+                                                (3, 1, 0.5, "systematic"), (513, 12, 0.0, "multinomial"),
+                                                (1025, 9, 1.0, "multinomial"), (255, 6, 1.0, "systematic")])
+def test_fused_edge_sizes_vs_oracle(golden, N, T, essrmin, scheme):
+    """Degenerate sizes (N = 1, 2, odd), T = 1, never / always resampling: same decisions and
+    summaries as the oracle with injected noise."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    y = lst(golden["data/sv_seed1_T1000"][:T])
+    z, u = make_noise(N, T, scheme, 21)
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, resampling=scheme, ESSrmin=essrmin,
+                noise=(z, u))
+    ref = orc.SMC(orc.Bootstrap(orc.StochVol(), y), N=N, resampling=scheme, ESSrmin=essrmin,
+                  noise=oracle_noise(z, u, scheme, N))
+    pf.run()
+    with np.errstate(all="ignore"):
+        ref.run()
+    assert pf.t == T and pf.summaries.rs_flags == ref.rs_flags
+    np.testing.assert_allclose(pf.summaries.ESSs, ref.ESSs, rtol=1e-10)
+    np.testing.assert_allclose(pf.summaries.logLts, ref.logLts, rtol=1e-11, atol=1e-10)
+    if scheme != "multinomial":
+        np.testing.assert_allclose(host(pf.X), ref.X, rtol=1e-11, atol=1e-13)
+    with pytest.raises(StopIteration):
+        next(pf)
+
+
+def test_degenerate_weights_follow_numpy_semantics(golden):
+    """An impossible observation (logG = -inf for every particle): NumPy gives NaN ESS / log_mean, the
+    strict `<` test is False (no resampling) and NaN propagates into logLt -- same here, no exception."""
+    import particles_b200 as pb
+    from particles_b200 import kalman, state_space_models as ssm
+    y = [np.array([0.1]), np.array([1e200]), np.array([0.2]), np.array([0.0])]
+    lg = kalman.LinearGauss(sigmaX=1.0, sigmaY=1e-3, rho=0.9)
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=lg, data=y), N=1000, seed=3)
+    pf.run()
+    assert np.isfinite(pf.summaries.logLts[0]) and pf.summaries.logLts[1] == -np.inf or np.isnan(pf.summaries.logLts[1])
+    assert all(np.isnan(v) or v == -np.inf for v in pf.summaries.logLts[2:])
+    assert pf.summaries.rs_flags[2] is False or pf.summaries.rs_flags[2] is True   # no exception is the point
