@@ -208,6 +208,17 @@ typedef struct {
                                   2 * world * 16 doubles) -> statistics are exchanged by the
                                   kernels themselves over NVLink and smcb_filter_step works */
     double *mail_peer[8];      /* every rank's mailbox as mapped in THIS process (own = mail_local) */
+    /* world > 1, optional: EXACT global resampling (mode 2).  X[0], X[1] and cdf
+       of every rank live in peer-mapped memory (smcb_p2p_alloc); on a resampling step each rank
+       searches the global CDF (shard offsets from the exchanged statistics + the owning shard's
+       local CDF) and pulls the selected ancestors over NVLink.  Needs mail_local; Feynman-Kac
+       kinds without auxiliary weights (bootstrap, guided); systematic or stratified. */
+    int32_t rs_global, reserved0;
+    double *stage_X;           /* (d, n) gathered ancestors of a global resampling step   */
+    double *stage_lw;          /* (n)    their restart log-weights                        */
+    const double *peer_X0[8];  /* rank r's X[0] / X[1] / cdf as mapped in THIS process    */
+    const double *peer_X1[8];
+    const double *peer_cdf[8];
 } smcb_filter_desc;
 
 int smcb_filter_create(smcb_ctx *ctx, const smcb_filter_desc *desc, smcb_filter **out);

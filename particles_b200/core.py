@@ -24,7 +24,7 @@ import torch
 from . import _lib
 from . import collectors
 from . import resampling as rs
-from .device import as_device, context, empty, ptr, require_cuda
+from .device import as_device, context, empty, ptr, require_cuda, tensor_from_ptr
 
 
 class FeynmanKac:
@@ -70,10 +70,14 @@ class _FusedEngine:
     """Owns the device buffers of one fused filter and the smcb_filter handle."""
 
     def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0,
-                 world=1, rank=0, group=None, p2p=False):
+                 world=1, rank=0, group=None, p2p=False, global_rs=False):
         self.world, self.rank, self.group = int(world), int(rank), group
         self.p2p = bool(p2p) and self.world > 1
+        self.global_rs = bool(global_rs) and self.world > 1
+        if self.global_rs and not self.p2p:
+            raise ValueError("global resampling over shards needs the peer-memory exchange (exchange='p2p')")
         self._mail_local, self._mail_peers = None, []
+        self._arena_local, self._arena_peers = None, []
         self.ctx = context()
         self.lib = self.ctx.lib
         self.N, self.T = int(N), int(spec["data"].shape[0])
@@ -82,10 +86,17 @@ class _FusedEngine:
         dev = self.ctx.device
         f64 = dict(dtype=torch.float64, device=dev)
         xshape = (n,) if self.dim == 1 else (self.dim, n)      # SoA: component-major
-        self.X = [torch.empty(xshape, **f64), torch.empty(xshape, **f64)]
+        if self.global_rs:      # particles and CDF in peer-mapped memory: peers pull ancestors from it
+            arena = self._open_arena((2 * self.dim + 1) * n * 8)
+            nd = self.dim * n
+            self.X = [tensor_from_ptr(arena, xshape), tensor_from_ptr(arena + nd * 8, xshape)]
+            self.cdf = tensor_from_ptr(arena + 2 * nd * 8, (n,))
+            self.stage_X, self.stage_lw = torch.empty(xshape, **f64), torch.empty(n, **f64)
+        else:
+            self.X = [torch.empty(xshape, **f64), torch.empty(xshape, **f64)]
+            self.cdf = torch.empty(n, **f64)
         self.lw = [torch.empty(n, **f64), torch.empty(n, **f64)]
         self.A = torch.empty(n, dtype=torch.int64, device=dev)
-        self.cdf = torch.empty(n, **f64)
         self.summ = torch.zeros((T, _lib.SUMMARY_STRIDE), **f64)
         # the observations are the only per-run host input of this path: pinned -> device
         self.data_host = torch.from_numpy(spec["data"].reshape(-1)).pin_memory()
@@ -122,6 +133,13 @@ class _FusedEngine:
             d.local_stats, d.gathered = self.local_stats.data_ptr(), self.gathered.data_ptr()
             if self.p2p:
                 self._open_mailboxes(d)
+            if self.global_rs:
+                nd = self.dim * n * 8
+                d.rs_global = 1
+                d.stage_X, d.stage_lw = self.stage_X.data_ptr(), self.stage_lw.data_ptr()
+                for r in range(self.world):
+                    base = self._arena_local if r == self.rank else self._arena_by_rank[r]
+                    d.peer_X0[r], d.peer_X1[r], d.peer_cdf[r] = base, base + nd, base + 2 * nd
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(self.ctx.handle, C.byref(d), C.byref(h)))
@@ -147,6 +165,26 @@ class _FusedEngine:
             self._mail_peers.append(pp.value)
             d.mail_peer[r] = pp.value
         dist.barrier(group=self.group)       # every mailbox is mapped before anybody writes
+
+    def _open_arena(self, nbytes):
+        """Global resampling: this rank's X[0] | X[1] | cdf in one IPC-shareable allocation, mapped by
+        every peer (same exchange of handles as the mailboxes)."""
+        import torch.distributed as dist
+        ptr_ = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        _lib.check(self.lib.smcb_p2p_alloc(self.ctx.handle, int(nbytes), C.byref(ptr_), hbuf))
+        self._arena_local = ptr_.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
+        self._arena_by_rank = {}
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            pp = C.c_void_p()
+            _lib.check(self.lib.smcb_p2p_open(self.ctx.handle, handles[r], C.byref(pp)))
+            self._arena_peers.append(pp.value)
+            self._arena_by_rank[r] = pp.value
+        return self._arena_local
 
     def step(self, nsteps=1):
         self.ctx.bind_stream()
@@ -185,6 +223,12 @@ class _FusedEngine:
                     self.lib.smcb_p2p_close(C.c_void_p(pp))
                 self.lib.smcb_p2p_free(C.c_void_p(self._mail_local))
                 self._mail_local, self._mail_peers = None, []
+            if self._arena_local:                    # after the barrier above: no peer still reads it
+                for pp in self._arena_peers:
+                    self.lib.smcb_p2p_close(C.c_void_p(pp))
+                self.X = self.cdf = None
+                self.lib.smcb_p2p_free(C.c_void_p(self._arena_local))
+                self._arena_local, self._arena_peers = None, []
 
     def __del__(self):
         try:

@@ -55,9 +55,11 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     const size_t part = (size_t)kMaxGrid * 8 * sizeof(double);
     char *mem;
     const size_t tpb = (size_t)(kMaxGrid + 8) * sizeof(double);
-    SMCB_CUDA(cudaMalloc(&mem, 256 + part + sb1 + sb2 + tpb + 64));
-    SMCB_CUDA(cudaMemsetAsync(mem, 0, 256 + part, c->stream));
-    SMCB_CUDA(cudaMemsetAsync(mem + 256 + part, 0xFF, sb1 + sb2, c->stream));
+    constexpr size_t kHdr = 512;       // FilterDev, then the two "last block done" tickets
+    static_assert(sizeof(FilterDev) <= 448, "FilterDev outgrew its header slot");
+    SMCB_CUDA(cudaMalloc(&mem, kHdr + part + sb1 + sb2 + tpb + 64));
+    SMCB_CUDA(cudaMemsetAsync(mem, 0, kHdr + part, c->stream));
+    SMCB_CUDA(cudaMemsetAsync(mem + kHdr + part, 0xFF, sb1 + sb2, c->stream));
     f->scan_mem = mem;
     f->st = reinterpret_cast<FilterDev *>(mem);
     FilterArgs &a = f->args;
@@ -73,9 +75,10 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     a.summaries = d->summaries;
     a.z_in = d->z_in; a.u_in = d->u_in;
     a.st = f->st;
-    a.partials = reinterpret_cast<double *>(mem + 256);
-    a.ticket = reinterpret_cast<unsigned int *>(mem + 128);
-    char *sp = mem + 256 + part;
+    a.partials = reinterpret_cast<double *>(mem + kHdr);
+    a.ticket = reinterpret_cast<unsigned int *>(mem + 448);
+    a.ticket2 = reinterpret_cast<unsigned int *>(mem + 456);
+    char *sp = mem + kHdr + part;
     a.scan.ticket = reinterpret_cast<unsigned int *>(sp);
     a.scan.agg = reinterpret_cast<unsigned long long *>(sp + 16);
     a.scan.cpref = a.scan.agg + scan_tiles(n);
@@ -88,7 +91,7 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     a.index_offset = d->index_offset; a.T = d->T;
     a.essrmin = d->essrmin;
     a.key = key_of(d->seed);
-    a.tile_pref = reinterpret_cast<double *>(mem + 256 + part + sb1 + sb2);
+    a.tile_pref = reinterpret_cast<double *>(mem + kHdr + part + sb1 + sb2);
     {   // persistent grid: one wave of resident CTAs, each owning a contiguous range of pairs
         int dev = 0, sms = kSMs;
         SMCB_CUDA(cudaGetDevice(&dev));
@@ -115,6 +118,27 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
             SMCB_REQUIRE(a.world <= 8, "smcb_filter_create: the peer mailbox supports at most 8 ranks");
             for (int r = 0; r < a.world; r++)
                 SMCB_REQUIRE(a.mail_peer[r] != nullptr, "smcb_filter_create: mail_peer[%d] is NULL", r);
+        }
+        a.rs_global = (a.world > 1 && d->rs_global) ? 1 : 0;
+        if (a.rs_global) {
+            SMCB_REQUIRE(a.mail_local != nullptr, "smcb_filter_create: global resampling needs the peer mailbox");
+            SMCB_REQUIRE((n & 1) == 0, "smcb_filter_create: global resampling needs an even shard size");
+            SMCB_REQUIRE(d->stage_X && d->stage_lw, "smcb_filter_create: global resampling needs stage_X / stage_lw");
+            if (d->fk == SMCB_FK_APF || d->fk == SMCB_FK_AUXBOOT) {
+                set_error("fused filter: global resampling over shards is built for Feynman-Kac kinds without "
+                          "auxiliary weights (bootstrap, guided)");
+                return SMCB_ENOSYS;
+            }
+            if (d->scheme != SMCB_RS_SYSTEMATIC && d->scheme != SMCB_RS_STRATIFIED) {
+                set_error("fused filter: global resampling over shards supports systematic and stratified");
+                return SMCB_ENOSYS;
+            }
+            a.stage_X = d->stage_X; a.stage_lw = d->stage_lw;
+            for (int r = 0; r < a.world; r++) {
+                SMCB_REQUIRE(d->peer_X0[r] && d->peer_X1[r] && d->peer_cdf[r],
+                             "smcb_filter_create: peer_X0 / peer_X1 / peer_cdf[%d] is NULL", r);
+                a.pX[r][0] = d->peer_X0[r]; a.pX[r][1] = d->peer_X1[r]; a.pcdf[r] = d->peer_cdf[r];
+            }
         }
     }
     {
@@ -256,6 +280,10 @@ extern "C" int smcb_filter_state(smcb_filter *f, double *out8) {
     SMCB_CUDA(cudaStreamSynchronize(f->ctx->stream));
     out8[0] = (double)h.t; out8[1] = (double)h.cur; out8[2] = (double)h.last_rs; out8[3] = h.logLt;
     out8[4] = h.ess; out8[5] = h.log_mean_w; out8[6] = h.wm; out8[7] = h.ws;
+    if (h.sync_timeout) {
+        set_error("sharded filter: a wait on a peer GPU's flag timed out (a rank died or fell out of step)");
+        return SMCB_ECUDA;
+    }
     return SMCB_OK;
 }
 

@@ -40,6 +40,10 @@ struct FilterDev {
     double am, as, aq;    // same for the auxiliary weights (APF); == w* otherwise
     double reset_c;       // APF: log_mean_exp(logetat, W), core.py:302
     long long t_stop;     // graph mode: the WHILE node keeps iterating while t < t_stop
+    // exact global resampling over shards: shard r owns [goff[r], goff[r+1]) of the global CDF
+    double goff[9], gpi[8];
+    int sync_timeout;     // a bounded peer wait expired (diagnostic; results are then invalid)
+    int pad2;
 };
 
 struct FilterArgs {
@@ -70,7 +74,23 @@ struct FilterArgs {
     double *tile_pref;    // (grid + 1) exclusive prefixes of the blocks' normalised weight mass
     double essrmin;
     Philox key;
+    // exact global resampling (world > 1): peers' particles and CDFs mapped over NVLink
+    int rs_global;
+    unsigned int *ticket2;
+    double *stage_X, *stage_lw;
+    const double *pX[8][2];
+    const double *pcdf[8];
 };
+
+// bounded spin on a flag another GPU raises (epoch counters only grow); ~4 s at 2 GHz
+__device__ __forceinline__ void wait_epoch(const volatile double *flag, double epoch, FilterDev *st) {
+    const long long t0 = clock64();
+    if (*reinterpret_cast<volatile int *>(&st->sync_timeout)) return;   // already broken: do not stall again
+    while (*flag < epoch) {
+        if (clock64() - t0 > 8000000000ll) { st->sync_timeout = 1; break; }
+    }
+    __threadfence_system();
+}
 
 __device__ __forceinline__ StepK step_consts(const FilterArgs &a, long long t) {
     StepK k;
@@ -119,7 +139,9 @@ __device__ __forceinline__ void finalize_step(const FilterArgs &a, const Lse3 &w
         //   sharded                : LSE_shard(aux) - LSE_all(w) + log(world): each shard resamples
         //                            locally and carries its share of the mass
         double rc = 0.0;
-        if (APF || a.world > 1)
+        if (a.rs_global)        // one global resampling: the reference's restart, from global sums
+            rc = APF ? (log(x.s) + x.m) - (log(w.s) + w.m) : 0.0;
+        else if (APF || a.world > 1)
             rc = (log(xl.s) + xl.m) - (log(w.s) + w.m) + log((double)a.world);
         st->reset_c = rc;
         int flag = (t + 1 < a.T) && (ess_aux < N * a.essrmin);    // strict <, NaN -> False
@@ -358,6 +380,157 @@ __global__ void __launch_bounds__(kBlock) k_scan_w(M model, FilterArgs a) {
         carry = carry_next;
         __syncthreads();
     }
+    if (a.rs_global) {
+        // tell every peer that this shard's CDF of step t is complete ("last block done" ticket,
+        // then one lane per peer raises the scan epoch in that peer's mailbox)
+        __shared__ bool s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicInc(a.ticket2, gridDim.x - 1) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last && tid < a.world) {
+            __threadfence_system();
+            double *slot = a.mail_peer[tid] + ((size_t)(t & 1) * a.world + a.rank) * 16;
+            *reinterpret_cast<volatile double *>(slot + 9) = (double)(t + 1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// exact global resampling over particle shards (mode 2; resampling.py:599-610
+// applied to the concatenation of all shards).  Output j of rank r is global offspring
+// index_offset + j: its grid point su is located in the global CDF in two levels -- shard k with
+// goff[k] <= su < goff[k+1] (offsets from the exchanged statistics, identical bits on every rank),
+// then v = (su - goff[k]) / gpi[k] in shard k's own normalised CDF, read over NVLink -- and the
+// ancestor's state is pulled from shard k's particle buffer.  Model-independent: the gathered
+// ancestors land in stage_X / stage_lw and the step kernel then runs its streaming branch on them.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int shard_of(const double *goff, const double *gpi, int world, double su) {
+    int k = 0;
+    while (k + 1 < world && su >= goff[k + 1]) k++;
+    while (k > 0 && !(gpi[k] > 0.0)) k--;
+    while (k + 1 < world && !(gpi[k] > 0.0)) k++;
+    return k;
+}
+
+template <int SCHEME>
+static __global__ void __launch_bounds__(kBlock) k_resample_global(FilterArgs a, int D) {
+    FilterDev *st = a.st;
+    if (!st->rs_flag) return;
+    constexpr int kStage = 2048;
+    __shared__ double s_su[2];
+    __shared__ __align__(16) double s_cdf[kStage];
+    __shared__ long long s_hi;
+    __shared__ double s_goff[9], s_gpi[8];
+    const long long t = st->t;
+    const int cur = st->cur, world = a.world;
+    if ((int)threadIdx.x < world)
+        wait_epoch(a.mail_local + ((size_t)(t & 1) * world + threadIdx.x) * 16 + 9, (double)(t + 1), st);
+    if ((int)threadIdx.x <= world) s_goff[threadIdx.x] = st->goff[threadIdx.x];
+    if ((int)threadIdx.x < world) s_gpi[threadIdx.x] = st->gpi[threadIdx.x];
+    __syncthreads();
+    const int64_t n = a.n, npairs = n >> 1;                // sharded filters have even n
+    const double M_ = (double)a.n_global;
+    const double reset_c = st->reset_c;
+    const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
+    double u_sys = 0.0;
+    if (SCHEME == SMCB_RS_SYSTEMATIC) {
+        if (uin) u_sys = uin[0];
+        else { double u1; uniform_pair(a.key, 0ull, (uint32_t)t, kPurposeUniform, u_sys, u1); }
+    }
+    const int64_t ntiles = (npairs + kBlock - 1) / kBlock;
+    const int64_t per = a.chunk / kBlock;
+    const int64_t tile_lo = (int64_t)blockIdx.x * per;
+    const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
+    int64_t lo = -1;
+    int lo_shard = -1;
+    for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
+        const int64_t p = tile * kBlock + threadIdx.x;
+        const int64_t k0 = 2 * tile * kBlock;
+        const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+        double su[2] = {2.0, 2.0};
+        if (p < npairs) {
+            const double g0 = (double)(a.index_offset + 2 * p);
+            if (SCHEME == SMCB_RS_SYSTEMATIC) {
+                su[0] = (u_sys + g0) / M_;
+                su[1] = (u_sys + (g0 + 1.0)) / M_;
+            } else {
+                double u0, u1;
+                if (uin) { u0 = uin[2 * p]; u1 = uin[2 * p + 1]; }
+                else uniform_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, kPurposeUniform, u0, u1);
+                su[0] = (u0 + g0) / M_;
+                su[1] = (u1 + (g0 + 1.0)) / M_;
+            }
+            if (2 * p == k0) s_su[0] = su[0];
+            if (2 * p + 1 == k1) s_su[1] = su[1];
+        }
+        __syncthreads();
+        const double su_first = s_su[0], su_last = s_su[1];
+        const int kf = shard_of(s_goff, s_gpi, world, su_first);
+        const int kl = shard_of(s_goff, s_gpi, world, su_last);
+        int ks[2] = {kf, kf};
+        int64_t an[2] = {0, 0};
+        if (kf == kl) {
+            // the whole tile draws from one shard: same staged search as the step kernel, on that
+            // shard's CDF with the grid points mapped into its local scale
+            const double *cdf = a.pcdf[kf];
+            const double off = s_goff[kf], pi = s_gpi[kf];
+            const double v0 = fmin((su[0] - off) / pi, 1.0), v1 = fmin((su[1] - off) / pi, 1.0);
+            const double v_first = fmin((su_first - off) / pi, 1.0), v_last = fmin((su_last - off) / pi, 1.0);
+            if (lo < 0 || lo_shard != kf) lo = block_lower_bound<kBlock>(cdf, 0, n, v_first);
+            if (lo > n - 1) lo = n - 1;
+            lo_shard = kf;
+            const int64_t sbase = lo & ~(int64_t)1;
+            const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
+            for (int i = 2 * threadIdx.x; i < cnt; i += 2 * kBlock) {
+                if (i + 1 < cnt) *reinterpret_cast<double2 *>(&s_cdf[i]) = ld2(cdf + sbase + i);
+                else s_cdf[i] = cdf[sbase + i];
+            }
+            __syncthreads();
+            const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= v_last);
+            int64_t hi = lo;
+            if (!covered) hi = block_lower_bound<kBlock>(cdf, lo, n, v_last);
+            if (p < npairs) {
+                if (covered) {
+                    int l0 = (int)(lo - sbase), h0 = cnt;
+                    while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < v0) l0 = mid + 1; else h0 = mid; }
+                    int l1 = l0, h1 = cnt;
+                    while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < v1) l1 = mid + 1; else h1 = mid; }
+                    an[0] = sbase + l0;
+                    an[1] = sbase + l1;
+                    if (2 * p + 1 == k1) s_hi = an[1];
+                } else {
+                    const int64_t hi1 = hi < n ? hi + 1 : n;
+                    an[0] = lower_bound(cdf, lo, hi1, v0);
+                    an[1] = lower_bound(cdf, an[0], hi1, v1);
+                }
+            }
+            __syncthreads();
+            lo = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
+        } else {
+            // the tile straddles a shard boundary (at most world - 1 tiles per rank): plain searches
+            if (p < npairs) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    ks[j] = shard_of(s_goff, s_gpi, world, su[j]);
+                    const double v = fmin((su[j] - s_goff[ks[j]]) / s_gpi[ks[j]], 1.0);
+                    an[j] = lower_bound(a.pcdf[ks[j]], 0, n, v);
+                }
+            }
+            lo = -1;
+        }
+        if (p < npairs) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int64_t aj = an[j] < n - 1 ? an[j] : n - 1;
+                const double *Xs = a.pX[ks[j]][cur];
+                for (int c = 0; c < D; c++) a.stage_X[(size_t)c * n + 2 * p + j] = Xs[(size_t)c * n + aj];
+                a.A[2 * p + j] = (long long)ks[j] * n + aj;     // ancestors are GLOBAL particle indices
+            }
+            st2(a.stage_lw + 2 * p, reset_c, reset_c);
+        }
+        __syncthreads();       // s_su / s_hi are rewritten by the next tile
+    }
 }
 
 // multinomial: exponential spacings z = cumsum(-log u), M + 1 of them (resampling.py:536)
@@ -412,12 +585,14 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
     const FilterDev *st = a.st;
     const long long t = st->t;
     const int cur = st->cur;
-    const bool rs = (MODE == 0) ? (st->rs_flag != 0) : (MODE == 2);
+    // after a global resampling the ancestors are already gathered (stage_X / stage_lw): stream them
+    const bool staged = a.rs_global && (st->rs_flag != 0);
+    const bool rs = (MODE == 0) ? (st->rs_flag != 0 && !a.rs_global) : (MODE == 2);
     const double reset_c = st->reset_c;
     const StepK k = step_consts(a, t);
     const StepK kprev = step_consts(a, t - 1);
-    const double *__restrict__ Xi = a.X[cur];
-    const double *__restrict__ lwi = a.lw[cur];
+    const double *__restrict__ Xi = staged ? a.stage_X : a.X[cur];
+    const double *__restrict__ lwi = staged ? a.stage_lw : a.lw[cur];
     double *__restrict__ Xo = a.X[cur ^ 1];
     double *__restrict__ lwo = a.lw[cur ^ 1];
     const int64_t n = a.n, npairs = (n + 1) >> 1;
@@ -637,6 +812,17 @@ __global__ void __launch_bounds__(kBlock) k_finish(FilterArgs a) {
             w = lse3_merge(w, Lse3{g[0], g[1], g[2]});
             x = lse3_merge(x, Lse3{g[4], g[5], g[6]});
         }
+        if (a.rs_global) {      // shard r's share of the global (auxiliary) weight mass, rank order
+            double run = 0.0;
+            for (int r = 0; r < a.world; r++) {
+                const volatile double *g = gath + (size_t)r * gstride;
+                const double pi = (g[4] == -CUDART_INF) ? 0.0 : g[5] * fexp(g[4] - x.m) / x.s;
+                a.st->goff[r] = run;
+                a.st->gpi[r] = pi;
+                run = run + pi;
+            }
+            a.st->goff[a.world] = run;
+        }
         const volatile double *me = gath + (size_t)a.rank * gstride;
         s_tot[0] = w; s_tot[1] = x;
         s_tot[2] = Lse3{me[0], me[1], me[2]};
@@ -702,6 +888,11 @@ static int launch_step_t(smcb_filter *f) {
         before();
         k_scan_spacings<<<f->grid_scan2, kBlock, 0, s>>>(f->args);
         after(2);
+        f->ctx->launches++;
+    }
+    if (f->args.rs_global) {
+        if (SCHEME == SMCB_RS_STRATIFIED) k_resample_global<SMCB_RS_STRATIFIED><<<f->grid_move, kBlock, 0, s>>>(f->args, M::D);
+        else k_resample_global<SMCB_RS_SYSTEMATIC><<<f->grid_move, kBlock, 0, s>>>(f->args, M::D);
         f->ctx->launches++;
     }
     before();

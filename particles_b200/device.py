@@ -89,3 +89,18 @@ def empty(n, dtype=torch.float64, device=None, like=None):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     return torch.empty(n, dtype=dtype, device=device)
+
+
+class _RawDeviceBuffer:
+    """Minimal ``__cuda_array_interface__`` carrier: lets torch view device memory it did not allocate
+    (peer-mapped arenas from ``smcb_p2p_alloc``).  The owner keeps the allocation alive."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def tensor_from_ptr(ptr, shape, dtype=torch.float64):
+    """A torch tensor over raw device memory (no copy, no ownership)."""
+    typestr = {torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+    return torch.as_tensor(_RawDeviceBuffer(ptr, shape, typestr), device=context().device)

@@ -13,6 +13,15 @@ unbiased without moving particles.  This is a different (also consistent) estima
 reference's single global resampling; logLt parity is statistical, and G = 1 reduces to the
 reference exactly.
 
+``resampling_mode="global"`` is the exact alternative (mode 2): ONE resampling
+over all N particles, as the reference does.  The shards' particles and CDFs live in peer-mapped
+memory; on a resampling step every rank locates its N/G grid points in the global CDF (shard
+offsets from the exchanged statistics, then the owning shard's CDF read over NVLink) and pulls
+the selected ancestors from the owner's buffer -- no host round trip, no variable-size
+collective; with balanced shards almost every pull is local.  Ancestors are global particle
+indices, weights restart at 0, and because Philox counters follow the global particle index a
+G-rank run reproduces the single-device run of the same seed up to rounding of the two-level CDF.
+
 The helpers at the bottom restate the merge / restart algebra on the host (NumPy); the gloo
 tests use them to check the scheme itself on CPU with world_size 2.
 """
@@ -27,7 +36,7 @@ class ShardedFilter(_FusedEngine):
     shards draws the same numbers as one big filter would."""
 
     def __init__(self, spec, n_local, scheme, ESSrmin, seed, rank, world, group=None, noise=None,
-                 exchange="p2p"):
+                 exchange="p2p", resampling_mode="island"):
         """``exchange``: "p2p" (default, <= 8 ranks of one node) -- the kernels exchange the
         statistics themselves through NVLink peer memory, the step loop runs without the host;
         "nccl" -- one ``all_gather_into_tensor`` per step issued from Python."""
@@ -35,9 +44,12 @@ class ShardedFilter(_FusedEngine):
             raise ValueError("sharded filters need an even number of particles per rank")
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if resampling_mode not in ("island", "global"):
+            raise ValueError("resampling_mode must be 'island' or 'global'")
         super().__init__(spec, n_local, scheme, ESSrmin, seed, noise=noise,
                          n_global=n_local * world, index_offset=rank * n_local,
-                         world=world, rank=rank, group=group, p2p=(exchange == "p2p" and world <= 8))
+                         world=world, rank=rank, group=group, p2p=(exchange == "p2p" and world <= 8),
+                         global_rs=(resampling_mode == "global"))
 
 
 class ShardedSMC:
@@ -46,7 +58,7 @@ class ShardedSMC:
     ``N_global = world * N``.  Stock (fused) models only."""
 
     def __init__(self, fk=None, N=100, resampling="systematic", ESSrmin=0.5, seed=0, group=None,
-                 exchange="p2p"):
+                 exchange="p2p", resampling_mode="island"):
         import time
         import torch.distributed as dist
         from .state_space_models import fused_spec
@@ -57,7 +69,7 @@ class ShardedSMC:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self._time = time
         self._engine = ShardedFilter(spec, N, resampling, ESSrmin, seed, self.rank, self.world, group,
-                                     exchange=exchange)
+                                     exchange=exchange, resampling_mode=resampling_mode)
         self.t, self.logLt, self.cpu_time = 0, 0.0, None
         self.ESSs, self.logLts, self.rs_flags = [], [], []
 
@@ -75,6 +87,12 @@ class ShardedSMC:
     @property
     def X(self):
         return self._engine.X[(self.t - 1) & 1]
+
+    @property
+    def A(self):
+        """Ancestors of the last resampling step: shard-local indices ("island"), global particle
+        indices ("global")."""
+        return self._engine.A
 
 
 # ---------------------------------------------------------------------------

@@ -43,6 +43,7 @@ def main():
         lls.append(float(tab[T - 1, 1]))
         nrs = int(tab[:, 2].sum())
         f.close()
+    global_mode_checks(fk, rank, world)
     ref = g["stat/sv_T1000_N100000/logLt"]            # reference runs at N = 1e5 (same total for world=2)
     mu, sd = ref.mean(), ref.std(ddof=1) * np.sqrt(100_000 / (n_local * world))
     if rank == 0:
@@ -57,6 +58,56 @@ def main():
         print("SHARDED OK")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def global_mode_checks(fk, rank, world):
+    """resampling_mode="global": ONE resampling over all shards (the reference's semantics).  Philox
+    counters follow the global particle index, so the G-rank run must reproduce the single-device run of
+    the same seed up to rounding of the two-level CDF (a handful of ancestors may flip)."""
+    from particles_b200 import state_space_models as ssm
+    from particles_b200.core import _FusedEngine
+    from particles_b200.parallel import ShardedFilter
+    spec = ssm.fused_spec(fk)
+    n_local, Tg = 60_000, 300
+    for scheme in ("systematic", "stratified"):
+        f = ShardedFilter(spec, n_local, scheme, 0.5, 77, rank, world, resampling_mode="global")
+        f.step(Tg)
+        f.state()                                   # raises if a peer wait timed out
+        tab = f.summ[:Tg].clone()
+        Xl, A = f.X[(Tg - 1) & 1].clone(), f.A.clone()
+        Xs = [torch.empty_like(Xl) for _ in range(world)]
+        dist.all_gather(Xs, Xl)
+        ends = torch.stack([A[0], A[-1]])
+        all_ends = [torch.empty_like(ends) for _ in range(world)]
+        dist.all_gather(all_ends, ends)
+        assert bool((A[1:] >= A[:-1]).all()) and int(A.min()) >= 0 and int(A.max()) < n_local * world
+        for r in range(world - 1):                  # sorted across ranks too
+            assert int(all_ends[r][1]) <= int(all_ends[r + 1][0])
+        f.close()
+        if rank == 0:
+            e = _FusedEngine(spec, n_local * world, scheme, 0.5, 77)
+            e.step(Tg)
+            one = e.summ[:Tg].clone()
+            assert torch.equal(one[:, 2], tab[:, 2]), "resampling decisions differ from the single-device run"
+            nrs = int(tab[:, 2].sum())
+            assert nrs >= 10
+            assert torch.allclose(one[:, 0], tab[:, 0], rtol=1e-4), (one[:, 0] - tab[:, 0]).abs().max()
+            assert torch.allclose(one[:, 1], tab[:, 1], rtol=0, atol=1e-5), (one[:, 1] - tab[:, 1]).abs().max()
+            Xg, X1 = torch.cat(Xs), e.X[(Tg - 1) & 1]
+            frac = float((~torch.isclose(Xg, X1, rtol=1e-9, atol=1e-12)).double().mean())
+            print("global", scheme, "resamplings", nrs, "max |dlogLt|", float((one[:, 1] - tab[:, 1]).abs().max()),
+                  "fraction of particles that differ", frac)
+            assert frac < 1e-3
+            e.close()
+        dist.barrier()
+    # combinations that are not built say so
+    try:
+        ShardedFilter(ssm.fused_spec(ssm.AuxiliaryPF(ssm=ssm.StochVol(), data=fk.data)), 1000, "systematic", 0.5, 1,
+                      rank, world, resampling_mode="global")
+        raise AssertionError("APF + global resampling should raise")
+    except NotImplementedError:
+        pass
+    dist.barrier()
 
 
 if __name__ == "__main__":
