@@ -220,7 +220,7 @@ def run_b200(args):
         sp["data"] = y[:nsteps].reshape(-1, 1).copy()
         if world == 1:
             return _FusedEngine(sp, n, SCHEME, ESSRMIN, seed)
-        return ShardedFilter(sp, n, SCHEME, ESSRMIN, seed, rank, world)
+        return ShardedFilter(sp, n, SCHEME, ESSRMIN, seed, rank, world, resampling_mode=args.resampling_mode)
 
     def barrier():
         if world > 1:
@@ -304,7 +304,7 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         sp = ShardedSMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y_host), N=n, resampling=SCHEME,
-                        ESSrmin=ESSRMIN, seed=77)
+                        ESSrmin=ESSRMIN, seed=77, resampling_mode=args.resampling_mode)
         sp.run()
         ll = sp.logLt
         barrier()
@@ -336,7 +336,8 @@ def run_b200(args):
                                "(BASELINE config 2" + (")" if world == 1 else "/4, particle-sharded)"),
                    "l2": "working set 4 x 80 MB of fp64 state per GPU > 126 MB L2 (no flush needed)",
                    "resampling_steps": n_rs, "logLt": logLt,
-                   "parallelism": "single GPU" if world == 1 else f"particles sharded over {world} GPUs"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"particles sharded over {world} GPUs, {args.resampling_mode} resampling"},
         "gpu_launches": launches,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
     }
@@ -353,6 +354,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--resampling-mode", default="island", choices=["island", "global"],
+                    help="N > 1 GPUs: per-shard resampling with mass carry (default) or one exact global "
+                         "resampling with ancestors pulled over NVLink")
     ap.add_argument("--essrmin", type=float, default=0.5,
                     help="0.5 = BASELINE config 2; 1.0 = resample at every step (stress case)")
     args = ap.parse_args()

@@ -414,7 +414,7 @@ __device__ __forceinline__ int shard_of(const double *goff, const double *gpi, i
 }
 
 template <int SCHEME>
-static __global__ void __launch_bounds__(kBlock) k_resample_global(FilterArgs a, int D) {
+static __global__ void __launch_bounds__(kBlock, 3) k_resample_global(FilterArgs a, int D) {
     FilterDev *st = a.st;
     if (!st->rs_flag) return;
     constexpr int kStage = 2048;
@@ -495,7 +495,12 @@ static __global__ void __launch_bounds__(kBlock) k_resample_global(FilterArgs a,
                     int l0 = (int)(lo - sbase), h0 = cnt;
                     while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < v0) l0 = mid + 1; else h0 = mid; }
                     int l1 = l0, h1 = cnt;
-                    while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < v1) l1 = mid + 1; else h1 = mid; }
+#pragma unroll
+                    for (int w = 0; w < 4; w++)
+                        if (l1 < cnt && s_cdf[l1] < v1) l1++;
+                    if (l1 < cnt && s_cdf[l1] < v1) {
+                        while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < v1) l1 = mid + 1; else h1 = mid; }
+                    }
                     an[0] = sbase + l0;
                     an[1] = sbase + l1;
                     if (2 * p + 1 == k1) s_hi = an[1];
@@ -520,13 +525,12 @@ static __global__ void __launch_bounds__(kBlock) k_resample_global(FilterArgs a,
             lo = -1;
         }
         if (p < npairs) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int64_t aj = an[j] < n - 1 ? an[j] : n - 1;
-                const double *Xs = a.pX[ks[j]][cur];
-                for (int c = 0; c < D; c++) a.stage_X[(size_t)c * n + 2 * p + j] = Xs[(size_t)c * n + aj];
-                a.A[2 * p + j] = (long long)ks[j] * n + aj;     // ancestors are GLOBAL particle indices
-            }
+            const int64_t a0 = an[0] < n - 1 ? an[0] : n - 1, a1 = an[1] < n - 1 ? an[1] : n - 1;
+            const double *X0 = a.pX[ks[0]][cur], *X1 = a.pX[ks[1]][cur];
+            for (int c = 0; c < D; c++)
+                st2(a.stage_X + (size_t)c * n + 2 * p, __ldg(X0 + (size_t)c * n + a0), __ldg(X1 + (size_t)c * n + a1));
+            // ancestors are GLOBAL particle indices
+            *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2((long long)ks[0] * n + a0, (long long)ks[1] * n + a1);
             st2(a.stage_lw + 2 * p, reset_c, reset_c);
         }
         __syncthreads();       // s_su / s_hi are rewritten by the next tile
