@@ -574,6 +574,12 @@ static __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 #ifndef SMCB_MINB
 #define SMCB_MINB 3
 #endif
+// 1: the CDF slice of a resampling tile is brought in by ONE TMA bulk copy (cp.async.bulk + mbarrier),
+//    double-buffered: the slice of tile i+1 is in flight while tile i propagates and reweights.
+// 0: all threads stage it with 16-byte loads (kept for A/B timing, profiles/).
+#ifndef SMCB_TMA_STAGE
+#define SMCB_TMA_STAGE 1
+#endif
 // MODE 0: both branches, chosen at run time from FilterDev.rs_flag.  MODE 1 / 2 compile the identity /
 // resampling branch alone (own register allocation); measured no faster than MODE 0 (DESIGN.md
 // section 6), so only MODE 0 is instantiated.
@@ -584,7 +590,12 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
     constexpr int kStage = (MODE == 1) ? 2 : 2048;     // doubles of CDF staged per output tile
     __shared__ Lse3 smem[kBlock / 32];
     __shared__ double s_su[2];
+#if SMCB_TMA_STAGE
+    __shared__ __align__(128) double s_cdf2[2][kStage];
+    __shared__ __align__(8) uint64_t s_bar[2];
+#else
     __shared__ __align__(16) double s_cdf[kStage];
+#endif
     __shared__ long long s_hi;
     const FilterDev *st = a.st;
     const long long t = st->t;
@@ -697,6 +708,25 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
         const int64_t tile_lo = (int64_t)blockIdx.x * per;
         const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
         int64_t lo = -1;
+#if SMCB_TMA_STAGE
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init_fence(); }
+        __syncthreads();
+        uint32_t phase0 = 0, phase1 = 0;
+        int buf = 0;
+        // thread 0: bring cdf[sb, sb + c) into buffer b (sb = lo_ rounded down to even => 16-byte aligned)
+        auto issue = [&](int64_t lo_, int b) {
+            const int64_t sb = lo_ & ~(int64_t)1;
+            const int c = (int)((n - sb) < kStage ? (n - sb) : kStage);
+            const uint32_t bytes = (uint32_t)(c & ~1) * 8u;
+            if (c & 1) s_cdf2[b][c - 1] = a.cdf[sb + c - 1];      // odd tail (n odd, end of the array)
+            if (bytes) {
+                mbar_arrive_expect_tx(&s_bar[b], bytes);
+                tma_bulk_g2s(&s_cdf2[b][0], a.cdf + sb, bytes, &s_bar[b]);
+            } else {
+                mbar_arrive(&s_bar[b]);
+            }
+        };
+#endif
         for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
             const int64_t p = tile * kBlock + threadIdx.x;
             const int64_t k0 = 2 * tile * kBlock;
@@ -723,6 +753,21 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
             }
             __syncthreads();
             const double su_first = s_su[0], su_last = s_su[1];
+#if SMCB_TMA_STAGE
+            if (lo < 0) {                                      // first tile of this block
+                lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
+                lo = lo < n - 1 ? lo : n - 1;
+                if (threadIdx.x == 0) issue(lo, buf);
+                __syncthreads();
+            }
+            // the slice of the CDF this tile's outputs fall into was requested while the previous tile
+            // was propagating (TMA bulk copy, 16 KB); su is sorted, so the slice starts at `lo`
+            const int64_t sbase = lo & ~(int64_t)1;
+            const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
+            mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
+            if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+            const double *s_cdf = s_cdf2[buf];
+#else
             if (lo < 0) lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
             // stage the slice of the CDF this tile's outputs fall into (16 KB, coalesced 16-byte
             // loads) and search it in shared memory; su is sorted, so the slice starts at `lo`
@@ -733,11 +778,12 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
                 else s_cdf[i] = a.cdf[sbase + i];
             }
             __syncthreads();
+#endif
             const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= su_last);
             int64_t hi = lo;
             if (!covered) hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);   // rare: sparse mass
+            int64_t a0 = 0, a1 = 0;
             if (p < npairs) {
-                int64_t a0, a1;
                 if (covered) {
                     int l0 = (int)(lo - sbase), h0 = cnt;
                     while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < su[0]) l0 = mid + 1; else h0 = mid; }
@@ -759,6 +805,13 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
                     a0 = lower_bound(a.cdf, lo, hi1, su[0]);
                     a1 = lower_bound(a.cdf, a0, hi1, su[1]);
                 }
+            }
+#if SMCB_TMA_STAGE
+            __syncthreads();                                   // s_hi published; buffer buf^1 is free
+            const int64_t lo_next = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
+            if (tile + 1 < tile_hi && threadIdx.x == 0) issue(lo_next, buf ^ 1);
+#endif
+            if (p < npairs) {
                 a0 = a0 < n - 1 ? a0 : n - 1;
                 a1 = a1 < n - 1 ? a1 : n - 1;
                 double xp[2][D], base[2];
@@ -780,8 +833,13 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
                 lse3_add_batch<2>(acc[0], l);
                 if (APF) lse3_add_batch<2>(acc[K - 1], av);
             }
+#if SMCB_TMA_STAGE
+            lo = lo_next;
+            buf ^= 1;
+#else
             __syncthreads();
             lo = covered ? (s_hi < n ? s_hi : n - 1) : hi;
+#endif
         }
     }
 
