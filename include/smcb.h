@@ -73,6 +73,8 @@ int smcb_wmean_and_var(smcb_ctx *ctx, const double *W, const double *x, int64_t 
 #define SMCB_RS_STRATIFIED 1  /* resampling.py:599-603 */
 #define SMCB_RS_SYSTEMATIC 2  /* resampling.py:606-610 */
 #define SMCB_RS_RESIDUAL 3    /* resampling.py:613-627 */
+#define SMCB_RS_SSP 4         /* resampling.py:630-677; sequential recursion, one device thread;
+                                 u_in = N - 1 uniforms; synchronises once (ValueError check) */
 
 /* Inclusive prefix sum of non-negative fp64 values (the CDF that inverse_cdf,
  * resampling.py:484-509, walks).  Single pass, decoupled look-back with a

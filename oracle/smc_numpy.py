@@ -159,11 +159,71 @@ def residual(W, M, u=None):
     return A
 
 
+def ssp(W, M, u=None):
+    """particles/resampling.py:630-677 (Srinivasan sampling process).  State machine over two
+    active particles (a, b): at step k the fractional parts are pushed towards each other until one
+    of them reaches 0 (that particle retires with its integer part) or 1 (it retires with one more
+    offspring), and particle k + 2 enters.  ``u`` = the N - 1 uniforms of the process."""
+    N = W.shape[0]
+    MW = M * W
+    kids = np.floor(MW).astype(np.int64)
+    frac = MW - kids
+    if u is None:
+        u = np.random.rand(N - 1)
+    a, b = 0, 1
+    for k in range(N - 1):
+        up_a = min(frac[b], 1.0 - frac[a])      # mass a can take from b
+        up_b = min(frac[a], 1.0 - frac[b])      # mass b can take from a
+        tot = up_a + up_b
+        p_swap = up_a / tot if tot > 0.0 else 0.0
+        step = up_a
+        if u[k] < p_swap:                       # relabel so that `a` is always the one that grows
+            a, b = b, a
+            step = up_b
+        if frac[b] < 1.0 - frac[a]:             # b is emptied and retires
+            frac[a] += step
+            b = k + 2
+        else:                                   # a is filled: one more offspring, a retires
+            frac[b] -= step
+            kids[a] += 1
+            a = k + 2
+    if N > 1 and kids.sum() == M - 1:           # accumulated round-off may have lost one particle
+        last = a if b == N else b
+        if frac[last] > 0.99:
+            kids[last] += 1
+    if kids.sum() != M:
+        raise ValueError("ssp resampling: wrong size for output")
+    return np.arange(N).repeat(kids)
+
+
+def killing(W, M, u=None, u_multinomial=None):
+    """particles/resampling.py:680-697: keep particle i with probability W[i] / max W, otherwise
+    replace it by a multinomial draw; M = N only.  Draw order: rand(N), then the multinomial's."""
+    N = W.shape[0]
+    if M != N:
+        raise ValueError("killing resampling defined only for M=N")
+    if u is None:
+        u = np.random.rand(N)
+    dead = u * W.max() >= W
+    A = np.arange(N)
+    A[dead] = multinomial(W, int(dead.sum()), u_multinomial)
+    return A
+
+
+def multinomial_once(W, u=None):
+    """particles/resampling.py:573-597."""
+    if u is None:
+        u = np.random.rand()
+    return int(np.searchsorted(np.cumsum(W), u))
+
+
 RS_FUNCS = {
     "multinomial": multinomial,
     "stratified": stratified,
     "systematic": systematic,
     "residual": residual,
+    "ssp": ssp,
+    "killing": killing,
 }
 
 

@@ -12,7 +12,8 @@ SO_PATH = os.environ.get("SMCB_LIB") or os.path.join(HERE, "libsmcb.so")   # SMC
 SMCB_MAX_PARAMS = 256
 SUMMARY_STRIDE = 4
 
-RS_CODES = {"multinomial": 0, "stratified": 1, "systematic": 2, "residual": 3}
+RS_CODES = {"multinomial": 0, "stratified": 1, "systematic": 2, "residual": 3, "ssp": 4}
+FUSED_SCHEMES = ("multinomial", "stratified", "systematic")     # schemes built into the fused step kernel
 FK_BOOTSTRAP, FK_GUIDED, FK_APF, FK_AUXBOOT = 0, 1, 2, 3
 MODEL_STOCHVOL, MODEL_LINGAUSS, MODEL_GORDON, MODEL_THETALOGISTIC = 0, 1, 2, 3
 MODEL_BEARINGS, MODEL_MVLINGAUSS, MODEL_DISCRETECOX, MODEL_STOCHVOLLEV = 4, 5, 6, 7

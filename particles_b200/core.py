@@ -267,8 +267,8 @@ class SMC:
         if fused is not False:
             from .state_space_models import fused_spec
             spec = fused_spec(fk)
-            if spec is not None and resampling == "residual":
-                spec = None                      # residual is not fused: plugin path
+            if spec is not None and resampling not in _lib.FUSED_SCHEMES:
+                spec = None                      # residual, ssp, killing, ...: plugin path (stand-alone kernels)
             if spec is None and fused is True:
                 raise NotImplementedError("this Feynman-Kac model has no fused kernel")
         if spec is not None:

@@ -523,8 +523,79 @@ __global__ void __launch_bounds__(kBlock) k_search_residual(const double *__rest
     }
 }
 
+// SSP resampling (Srinivasan sampling process, resampling.py:630-677): the pairwise process is a
+// sequential recursion over the particles (each step depends on which of the two active indices
+// survived the previous one), so ONE thread walks it with the two active (index, fractional part,
+// offspring count) triples in registers -- same operations in the same order as the reference,
+// hence identical offspring counts for the same uniforms.  O(N) serial: a completeness feature,
+// not a hot path.  status[0] = sum of the offspring counts after the reference's round-off fix.
+struct LoadCounts {
+    const long long *c;
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, long long (&v)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (i0 + j < n) ? c[i0 + j] : 0ll;
+    }
+};
+
+__global__ void k_ssp_counts(const double *__restrict__ W, int64_t n, int64_t m, const double *__restrict__ u,
+                             long long *__restrict__ nr, long long *__restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double M = (double)m;
+    auto split = [&](int64_t idx, double &xi, long long &cnt) {
+        const double mw = M * W[idx];
+        const double fl = floor(mw);
+        cnt = (long long)fl;
+        xi = mw - fl;
+    };
+    long long total = 0;
+    if (n == 1) {
+        double x; long long c0;
+        split(0, x, c0);
+        nr[0] = c0;
+        status[0] = c0;
+        return;
+    }
+    int64_t i = 0, j = 1;
+    double xi_i, xi_j;
+    long long c_i, c_j;
+    split(0, xi_i, c_i);
+    split(1, xi_j, c_j);
+    for (int64_t k = 0; k < n - 1; k++) {
+        double delta_i = fmin(xi_j, 1.0 - xi_i);          // increase i, decrease j
+        const double delta_j = fmin(xi_i, 1.0 - xi_j);    // the opposite
+        const double sum_delta = delta_i + delta_j;
+        const double pj = sum_delta > 0.0 ? delta_i / sum_delta : 0.0;
+        if (u[k] < pj) {                                  // swap, so that we always increase i
+            const int64_t ti = i; i = j; j = ti;
+            const double tx = xi_i; xi_i = xi_j; xi_j = tx;
+            const long long tc = c_i; c_i = c_j; c_j = tc;
+            delta_i = delta_j;
+        }
+        const int64_t nxt = k + 2;
+        if (xi_j < 1.0 - xi_i) {
+            xi_i += delta_i;
+            nr[j] = c_j; total += c_j;                    // j retires with its integer part
+            j = nxt;
+            if (nxt < n) split(nxt, xi_j, c_j); else { xi_j = 0.0; c_j = 0; }
+        } else {
+            xi_j -= delta_i;
+            c_i += 1;
+            nr[i] = c_i; total += c_i;                    // i retires with one more offspring
+            i = nxt;
+            if (nxt < n) split(nxt, xi_i, c_i); else { xi_i = 0.0; c_i = 0; }
+        }
+    }
+    // the index that is still in range keeps its count; round-off may have lost one particle
+    const int64_t last = (j == n) ? i : j;
+    double xl = (j == n) ? xi_i : xi_j;
+    long long cl = (j == n) ? c_i : c_j;
+    if (total + cl == m - 1 && xl > 0.99) cl += 1;
+    nr[last] = cl;
+    status[0] = total + cl;
+}
+
 extern "C" int64_t smcb_resample_scratch_doubles(int64_t n, int64_t m) {
-    return 2 * n + 2 * (m + 2) + 16;
+    return 3 * n + 2 * (m + 2) + 24;
 }
 
 extern "C" int smcb_resample(smcb_ctx *c, int scheme, const double *W, int64_t n, int64_t m,
@@ -539,6 +610,30 @@ extern "C" int smcb_resample(smcb_ctx *c, int scheme, const double *W, int64_t n
     double *u = z + ((m + 3) & ~(int64_t)1);
     double *aux = u + ((m + 3) & ~(int64_t)1);
     int rc;
+    if (scheme == SMCB_RS_SSP) {
+        // scratch reuse: uniforms (n - 1) in the cdf slot | counts in aux | their scan + status behind it
+        double *us = cdf;
+        long long *nr = reinterpret_cast<long long *>(aux);
+        long long *cum = nr + ((n + 1) & ~(int64_t)1);
+        long long *status = cum + ((n + 1) & ~(int64_t)1);
+        if (u_in == nullptr) {
+            if (n > 1 && (rc = smcb_uniform(c, us, n - 1))) return rc;
+            u_in = us;
+        }
+        k_ssp_counts<<<1, 32, 0, c->stream>>>(W, n, m, u_in, nr, status);
+        c->launches++;
+        SMCB_CUDA(cudaGetLastError());
+        long long total = 0;
+        SMCB_CUDA(cudaMemcpyAsync(&total, status, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+        SMCB_CUDA(cudaStreamSynchronize(c->stream));
+        if (total != m) {                                 // resampling.py:674-676
+            set_error("ssp resampling: wrong size for output");
+            return SMCB_EINVAL;
+        }
+        if ((rc = run_scan<long long>(c, LoadCounts{nr}, n, cum))) return rc;
+        LAUNCH(c, k_repeat, grid_for(m, kBlock * 4), kBlock, cum, n, m, A_out);
+        return SMCB_OK;
+    }
     const int64_t nu = (scheme == SMCB_RS_SYSTEMATIC) ? 1 : (scheme == SMCB_RS_STRATIFIED ? m : m + 1);
     if (u_in == nullptr) {
         if ((rc = smcb_uniform(c, u, nu))) return rc;

@@ -29,6 +29,8 @@ static int smcb_bind_1d(smcb_filter *f) {
     }
 }
 
+static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d);
+
 extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_filter **out) {
     SMCB_REQUIRE(c && d && out, "smcb_filter_create: NULL argument");
     SMCB_REQUIRE(d->n >= 1 && d->T >= 1, "smcb_filter_create: need n >= 1 and T >= 1");
@@ -46,8 +48,20 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     f->timed_ev = nullptr;
     f->timed_kind = nullptr;
     f->graph = nullptr; f->gexec = nullptr; f->has_graph = false; f->t_stop_host = 0;
+    f->scan_mem = nullptr;
+    const int rc = filter_setup(f, c, d);
+    if (rc) {                       // nothing of a half-built filter survives an error
+        if (f->scan_mem) cudaFree(f->scan_mem);
+        delete f;
+        return rc;
+    }
+    *out = f;
+    return SMCB_OK;
+}
+
+static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) {
     int rc = (d->dim == 1) ? smcb_bind_1d(f) : smcb_bind_nd(f);
-    if (rc) { delete f; return rc; }
+    if (rc) return rc;
 
     const int64_t n = d->n;
     const size_t sb1 = (scan_state_bytes(n) + 63) & ~(size_t)63;
@@ -58,9 +72,9 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     constexpr size_t kHdr = 512;       // FilterDev, then the two "last block done" tickets
     static_assert(sizeof(FilterDev) <= 448, "FilterDev outgrew its header slot");
     SMCB_CUDA(cudaMalloc(&mem, kHdr + part + sb1 + sb2 + tpb + 64));
+    f->scan_mem = mem;
     SMCB_CUDA(cudaMemsetAsync(mem, 0, kHdr + part, c->stream));
     SMCB_CUDA(cudaMemsetAsync(mem + kHdr + part, 0xFF, sb1 + sb2, c->stream));
-    f->scan_mem = mem;
     f->st = reinterpret_cast<FilterDev *>(mem);
     FilterArgs &a = f->args;
     memset(&a, 0, sizeof(a));
@@ -157,7 +171,6 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
             set_error("");
         }
     }
-    *out = f;
     return SMCB_OK;
 }
 

@@ -27,6 +27,7 @@ tests use them to check the scheme itself on CPU with world_size 2.
 """
 import numpy as np
 
+from . import _lib
 from .core import _FusedEngine
 
 
@@ -63,7 +64,7 @@ class ShardedSMC:
         import torch.distributed as dist
         from .state_space_models import fused_spec
         spec = fused_spec(fk)
-        if spec is None or resampling == "residual":
+        if spec is None or resampling not in _lib.FUSED_SCHEMES:
             raise NotImplementedError("sharded runs need a fused model and a fused resampling scheme")
         self.fk, self.N = fk, N
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)

@@ -17,7 +17,8 @@ from .device import as_device, context, empty, ptr
 
 __all__ = ["Weights", "exp_and_normalise", "essl", "log_sum_exp", "log_sum_exp_ab",
            "log_mean_exp", "wmean_and_var", "resampling", "rs_funcs", "inverse_cdf",
-           "uniform_spacings", "multinomial", "stratified", "systematic", "residual", "cumsum"]
+           "uniform_spacings", "multinomial", "stratified", "systematic", "residual", "cumsum",
+           "ssp", "killing", "multinomial_iid", "multinomial_once", "idiotic"]
 
 
 def _scalar(ctx, fn, *args):
@@ -183,7 +184,7 @@ def _resample(scheme, W, M, u=None, return_scratch=False):
     scratch = empty(int(ctx.lib.smcb_resample_scratch_doubles(n, M)), like=W)
     ud = None
     if u is not None:                      # injected uniforms, in the reference's draw order
-        ud = torch.ones(M + 2, dtype=torch.float64, device=W.device)
+        ud = torch.ones(max(M, n) + 2, dtype=torch.float64, device=W.device)
         uu = as_device(u).reshape(-1)
         ud[: uu.shape[0]] = uu
     _lib.check(ctx.lib.smcb_resample(ctx.handle, _lib.RS_CODES[scheme], ptr(W), n, M, ptr(A),
@@ -206,6 +207,66 @@ multinomial = _scheme("multinomial")
 stratified = _scheme("stratified")
 systematic = _scheme("systematic")
 residual = _scheme("residual")
+ssp = _scheme("ssp")                       # resampling.py:630-677 (sequential on the device, see smcb.h)
+
+
+def _register(f):
+    def g(W, M=None, **kw):
+        W = as_device(W)
+        return f(W, W.shape[0] if M is None else int(M), **kw)
+    g.__name__, g.__doc__ = f.__name__, f.__doc__
+    rs_funcs[f.__name__] = g
+    return g
+
+
+def _uniforms(n, like):
+    ctx = context(like.device)
+    u = empty(n, like=like)
+    _lib.check(ctx.lib.smcb_uniform(ctx.handle, ptr(u), n))
+    return u
+
+
+@_register
+def multinomial_iid(W, M, u=None, u_perm=None):
+    """particles/resampling.py:560-570: multinomial resampling followed by a uniformly random
+    permutation (argsort of M device uniforms), so that the indices are IID."""
+    A = _resample("multinomial", W, M, u)
+    keys = _uniforms(M, W) if u_perm is None else as_device(u_perm)
+    return A[torch.argsort(keys)]
+
+
+def multinomial_once(W, u=None):
+    """particles/resampling.py:573-597: one draw, ``searchsorted(cumsum(W), rand())``."""
+    W = as_device(W)
+    su = _uniforms(1, W) if u is None else as_device(np.atleast_1d(u))
+    ctx = context(W.device)
+    cdf = cumsum(W)
+    A = empty(1, dtype=torch.int64, like=W)
+    # the reference does not clip: a draw above cdf[-1] returns N; searchsorted here clips to N - 1
+    _lib.check(ctx.lib.smcb_searchsorted(ctx.handle, ptr(cdf), W.shape[0], ptr(su), 1, ptr(A)))
+    return int(A.item())
+
+
+@_register
+def killing(W, M, u=None, u_multinomial=None):
+    """particles/resampling.py:680-697: particle i survives with probability W[i] / max(W), otherwise it
+    is replaced by a multinomial draw.  Defined only for M = N (ValueError otherwise, as the reference)."""
+    n = W.shape[0]
+    if M != n:
+        raise ValueError("killing resampling defined only for M=N")
+    uu = _uniforms(n, W) if u is None else as_device(u)
+    killed = uu * W.max() >= W
+    nkilled = int(killed.sum().item())              # sizes the multinomial draw: one host read
+    A = torch.arange(n, dtype=torch.int64, device=W.device)
+    if nkilled:
+        A[killed] = _resample("multinomial", W, nkilled, u_multinomial)
+    return A
+
+
+@_register
+def idiotic(W, M, u=None):
+    """particles/resampling.py:700-707 (testing only): every offspring is the same single draw."""
+    return torch.full((M,), multinomial_once(W, u), dtype=torch.int64, device=W.device)
 
 
 def resampling(scheme, W, M=None):

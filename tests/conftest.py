@@ -21,5 +21,10 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_rs_extra():
+    return np.load(os.path.join(GOLDEN_DIR, "golden_rs_extra.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_stats():
     return np.load(os.path.join(GOLDEN_DIR, "golden_stats.npz"))

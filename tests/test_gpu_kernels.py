@@ -213,6 +213,52 @@ def test_resampling_vs_reference_injected_uniforms(pb, golden, name, scheme):
         assert bad.size <= max(1, M // 500) and np.all(np.abs(A[bad] - ref[bad]) <= 1)
 
 
+@pytest.mark.parametrize("name", RS_CASES)
+def test_ssp_killing_iid_vs_reference(pb, golden, golden_rs_extra, name):
+    """The schemes outside the fused kernel (resampling.py:560-570, 630-697) with the reference's uniforms."""
+    from particles_b200 import resampling as rs
+    W, M = golden[f"rs/{name}/W"], int(golden[f"rs/{name}/M"][0])
+    n, x = W.shape[0], golden_rs_extra
+    A = host(rs.ssp(dev(W), M=M, u=x[f"rs/{name}/ssp/u"]))
+    assert A.dtype == np.int64 and np.array_equal(A, x[f"rs/{name}/ssp/A"])     # same recursion, same bits
+    A2 = host(rs.resampling("ssp", dev(W), M=M))                                  # device uniforms
+    cnt = np.bincount(A2, minlength=n)
+    assert A2.shape == (M,) and np.all(np.abs(cnt - M * W) < 1.0 + 1e-9) and np.all(np.diff(A2) >= 0)
+    if M == n:
+        K = host(rs.killing(dev(W), M=M, u=x[f"rs/{name}/killing/u"], u_multinomial=x[f"rs/{name}/killing/u_multinomial"]))
+        ref = x[f"rs/{name}/killing/A"]
+        bad = np.flatnonzero(K != ref)      # the multinomial stage's second scan may move a tie by one
+        assert bad.size <= max(1, M // 500) and np.all(np.abs(K[bad] - ref[bad]) <= 1)
+        kept = x[f"rs/{name}/killing/u"] * W.max() < W
+        assert np.array_equal(K[kept], np.arange(n)[kept])
+    else:
+        with pytest.raises(ValueError) as e:
+            rs.killing(dev(W), M=M)
+        assert str(e.value) == bytes(x["rs/killing_error"]).decode()
+    B = host(rs.multinomial_iid(dev(W), M=M))
+    assert B.shape == (M,) and B.min() >= 0 and B.max() < n and np.all(W[B] > 0)
+    a = rs.multinomial_once(dev(W), u=0.5)
+    assert a == min(int(np.searchsorted(np.cumsum(W), 0.5)), n - 1)
+    I = host(rs.idiotic(dev(W), M=M, u=0.5))
+    assert np.array_equal(I, np.full(M, a))
+
+
+def test_ssp_large_and_plugin_path(pb):
+    """ssp at N = 2e5 against the oracle's restatement (same uniforms -> identical ancestors), and a filter
+    run with resampling='ssp' (plugin path: fused kernels have no ssp branch)."""
+    import particles_b200
+    from particles_b200 import resampling as rs, state_space_models as ssm
+    r = np.random.RandomState(3)
+    n = 200_000
+    W = orc.exp_and_normalise(r.randn(n) * 2.0)
+    u = r.rand(n - 1)
+    assert np.array_equal(host(rs.ssp(dev(W), u=u)), orc.ssp(W, n, u=u))
+    x, y = ssm.StochVol().simulate(30)
+    pf = particles_b200.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=2000, resampling="ssp", seed=3)
+    pf.run()
+    assert not pf.fused and np.isfinite(pf.logLt) and any(pf.summaries.rs_flags)
+
+
 def test_unknown_scheme_raises(pb, golden):
     from particles_b200 import resampling as rs
     with pytest.raises(ValueError) as e:
