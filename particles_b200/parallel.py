@@ -130,3 +130,39 @@ def lse3_of(v):
     m = v.max()
     e = np.exp(v - m)
     return m, e.sum(), (e * e).sum()
+
+
+def shard_shares(aux_triples):
+    """Global resampling: shard r owns [goff[r], goff[r+1]) of the global CDF, gpi[r] = its share of the
+    total (auxiliary) weight mass -- what ``k_finish`` derives from the exchanged statistics (rank order,
+    sequential sums, so every rank holds the same bits)."""
+    M, S, _ = merge_lse3(aux_triples)
+    gpi = np.array([0.0 if m == -np.inf else s * np.exp(m - M) / S for (m, s, _q) in aux_triples])
+    goff = np.zeros(len(gpi) + 1)
+    for r, p in enumerate(gpi):
+        goff[r + 1] = goff[r] + p
+    return goff, gpi
+
+
+def global_ancestors(su, goff, gpi, local_cdfs):
+    """Two-level inverse CDF of ``k_resample_global``: grid point ``su`` -> shard k with
+    goff[k] <= su < goff[k+1] (empty shards skipped) -> position of (su - goff[k]) / gpi[k] in shard k's own
+    normalised CDF.  Returns GLOBAL particle indices k * n + a."""
+    su = np.asarray(su, dtype=np.float64)
+    world, n = len(gpi), len(local_cdfs[0])
+    k = np.zeros(su.shape, dtype=np.int64)
+    for r in range(1, world):
+        k += (su >= goff[r])
+    for _ in range(world):                               # step off empty shards (down first, then up)
+        k = np.where((k > 0) & ~(gpi[k] > 0.0), k - 1, k)
+    for _ in range(world):
+        k = np.where((k + 1 < world) & ~(gpi[k] > 0.0), k + 1, k)
+    A = np.empty(su.shape, dtype=np.int64)
+    for r in range(world):
+        sel = k == r
+        if not sel.any():
+            continue
+        v = np.minimum((su[sel] - goff[r]) / gpi[r], 1.0)
+        a = np.searchsorted(local_cdfs[r], v, side="left")
+        A[sel] = r * n + np.minimum(a, n - 1)
+    return A

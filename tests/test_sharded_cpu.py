@@ -1,6 +1,6 @@
 """world_size-2 gloo tests (CPU) of the sharded-filter protocol of particles_b200/parallel.py:
 the per-step all-gather of (max, sum exp, sum exp^2) triples, the rank-order merge, the
-island restart log-weight.  The shard arithmetic is done by the oracle (NumPy) here; the
+island restart log-weight, and the two-level CDF search of the exact global resampling mode.  The shard arithmetic is done by the oracle (NumPy) here; the
 device kernels implement the same algebra (csrc/smcb_filter.cu: k_finish / finalize_step)."""
 import os
 import socket
@@ -110,3 +110,70 @@ def test_island_filter_world2_gloo(golden):
     ref = np.array(ref)
     sd = max(ref.std(ddof=1), isl.std(ddof=1))
     assert abs(isl.mean() - ref.mean()) < 4 * sd * np.sqrt(2 / len(seeds)) + 0.05, (isl, ref)
+
+
+def _global_worker(rank, world, port, lw_all, u, q):
+    """One rank of a global systematic resampling: statistics and (standing in for the NVLink reads of
+    the device kernel) the shards' CDFs travel through gloo; each rank resolves its own N/G grid points."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = lw_all.shape[0] // world
+    lw = lw_all[rank * n:(rank + 1) * n]
+    mine = par.lse3_of(lw)
+    buf = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(buf, torch.tensor(mine, dtype=torch.float64))
+    triples = [tuple(b.tolist()) for b in buf]
+    goff, gpi = par.shard_shares(triples)
+    cdf = np.cumsum(np.exp(lw - mine[0]) / mine[1])            # the shard's own normalised CDF (k_scan_w)
+    cdfs = [torch.zeros(n, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(cdfs, torch.from_numpy(cdf))
+    N = n * world
+    su = (u + np.arange(rank * n, (rank + 1) * n)) / N         # this rank's slice of the global grid
+    A = par.global_ancestors(su, goff, gpi, [c.numpy() for c in cdfs])
+    q.put((rank, A, goff, gpi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("skew", [0.0, 6.0])
+def test_global_resampling_two_level_search_world2_gloo(skew):
+    """The union of the ranks' ancestors equals ONE systematic resampling of all particles (reference
+    semantics, resampling.py:606-610) up to ties within rounding of the two-level CDF; shards with very
+    different masses (skew) make many grid points cross the shard boundary."""
+    world, n = 2, 5000
+    r = np.random.RandomState(4)
+    lw = r.randn(world * n) * 2.0
+    lw[:n] += skew                                              # shard 0 holds almost all the mass
+    u = r.rand(1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_global_worker, args=(k, world, port, lw, u, q)) for k in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        k, A, goff, gpi = q.get(timeout=300)
+        got[k] = (A, goff, gpi)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])   # same offsets everywhere
+    assert abs(got[0][1][-1] - 1.0) < 1e-12
+    A = np.concatenate([got[0][0], got[1][0]])
+    ref = orc.systematic(orc.exp_and_normalise(lw), world * n, u=u)
+    assert np.all(np.diff(A) >= 0) and A.min() >= 0 and A.max() < world * n
+    bad = np.flatnonzero(A != ref)
+    assert bad.size <= 2 and np.all(np.abs(A[bad] - ref[bad]) <= 1), (bad.size,)
+    if skew:
+        assert (got[1][0] < n).mean() > 0.9                     # rank 1 pulls most ancestors from shard 0
+
+
+def test_global_ancestors_skips_empty_shards():
+    goff, gpi = par.shard_shares([par.lse3_of(np.zeros(4)), (-np.inf, 0.0, 0.0), par.lse3_of(np.zeros(4))])
+    assert gpi[1] == 0.0 and goff[1] == goff[2] == 0.5
+    cdfs = [np.arange(1, 5) / 4.0, np.full(4, np.nan), np.arange(1, 5) / 4.0]
+    su = (0.3 + np.arange(12)) / 12
+    A = par.global_ancestors(su, goff, gpi, cdfs)
+    W = np.concatenate([np.full(4, 0.125), np.zeros(4), np.full(4, 0.125)])
+    assert np.array_equal(A, orc.systematic(W, 12, u=np.array([0.3])))
