@@ -6,6 +6,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 C=particles_b200/csrc
+mkdir -p particles_b200/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC \
      -DSMCB_BENCH_ONLY "$@" -c $C/smcb_filter.cu -o /tmp/smcb_filter_$name.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o particles_b200/variants/libsmcb_$name.so \
