@@ -2,6 +2,7 @@
 # build_variant.sh NAME [-DFLAG ...]: kernel-variant library for A/B timing.  Recompiles only smcb_filter.cu
 # (config-2 instantiation, -DSMCB_BENCH_ONLY) with the extra flags and links it with the objects of the last
 # full build -> particles_b200/variants/libsmcb_NAME.so; select it with SMCB_LIB=... python bench.py
+# The directory is git-ignored but travels with the gpurun snapshot (~28 MB per library): delete it after the run.
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
