@@ -37,15 +37,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=None, out=None):
+    """``extra`` (or env SMCB_NVCC_EXTRA, space separated) appends compile flags, e.g. "-DSMCB_TABLE_MATH=1";
+    ``out`` (or env SMCB_BUILD_OUT) names the library to write -- a FULL kernel-variant build next to the
+    default one (select it with SMCB_LIB=<out>); the default library is untouched."""
+    extra = extra if extra is not None else os.environ.get("SMCB_NVCC_EXTRA", "").split()
+    out = out or os.environ.get("SMCB_BUILD_OUT") or SO
+    variant = bool(extra) or os.path.abspath(out) != os.path.abspath(SO)
+    if not variant and not force and not needs_build():
         return SO
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra)
+    tag = ".variant" if variant else ""
+    os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
     from concurrent.futures import ThreadPoolExecutor
 
     def compile_one(src):
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
@@ -53,9 +61,9 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:      # translation units in parallel
         objs = list(pool.map(compile_one, SOURCES))
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out]
                           + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    return SO
+    return out
 
 
 if __name__ == "__main__":

@@ -7,8 +7,22 @@
 // (gen_coeffs.py), total error <= ~1.5 ulp; checked against NumPy/mpmath in
 // tests/test_gpu_kernels.py::test_device_math.
 #pragma once
+#ifndef SMCB_MATH_HOST_TEST      // tests/math_host.cpp compiles this header for the CPU with its own shim
 #include "smcb_common.cuh"
+#endif
 #include "smcb_math_coeffs.inc"
+
+// SMCB_TABLE_MATH=1: table-assisted exp and log (shorter polynomials, one L1-resident table load each):
+//   exp: 1024-entry table of 2^(j/1024) + degree-4 polynomial  (11 -> 4 dependent DFMAs)
+//   log: 256-entry table of {1/c, -log(1/c)} + degree-6 log1p  (no fp64 division)
+// Same accuracy class (<= ~1.5 ulp, tests/test_math_host.py checks both builds on the CPU).  Off by
+// default until timed on the device against the polynomial-only build (profiles/build_variant.sh).
+#ifndef SMCB_TABLE_MATH
+#define SMCB_TABLE_MATH 0
+#endif
+#if SMCB_TABLE_MATH
+#include "smcb_math_tables.inc"
+#endif
 
 namespace smcb {
 
@@ -51,6 +65,49 @@ __device__ __forceinline__ double horner(const double (&c)[N], double x) {
 #endif
 }
 
+#if SMCB_TABLE_MATH
+// exp(x) without range selects: x = (k/1024) ln2 + r, exp(x) = 2^(k >> 10) * T[k & 1023] * P4(r)
+__device__ __forceinline__ double fexp_core(double x) {
+    const double t = fma(x, 1024.0 * SMCB_LOG2E, kRintMagic);
+    const double kd = t - kRintMagic;
+    const int k = __double2loint(t);                       // |k| < 2^20 for |x| <= 709
+    double r = fma(kd, -(SMCB_LN2_HI / 1024.0), x);        // power-of-two scalings of the split: exact
+    r = fma(kd, -(SMCB_LN2_LO / 1024.0), r);
+    const double tj = __ldg(&kExp2Tab[k & 1023]);
+    // exp(r) - 1 = r + r^2 (c2 + c3 r + c4 r^2); T + T * (exp(r) - 1) keeps the table value's half ulp
+    double h = fma(kExp4C[4], r, kExp4C[3]);
+    h = fma(h, r, kExp4C[2]);
+    const double em1 = fma(r * r, h, r);
+    return fma(tj, em1, tj) * __hiloint2double(((k >> 10) + 1023) << 20, 0);
+}
+__device__ __forceinline__ double fexp(double x) {
+    double res = fexp_core(x);
+    res = (x < -708.0) ? 0.0 : res;
+    res = (x > 709.0) ? CUDART_INF : res;
+    return res;
+}
+__device__ __forceinline__ double fexp_neg(double x) {
+    const double res = fexp_core(x);
+    return (x < -708.0) ? 0.0 : res;
+}
+__device__ __forceinline__ double fexp_mid(double x) { return fexp_core(x); }
+
+// log(x) for positive NORMAL x: m in [sqrt(1/2), sqrt(2)) -> table interval j, r = m / c_j - 1, |r| <= 2^-7
+__device__ __forceinline__ double flog_pos(double x) {
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000FFFFF) | 0x3FF00000;
+    const bool big = hi > 0x3FF6A09E;
+    hi = big ? hi - 0x00100000 : hi;
+    e = big ? e + 1 : e;
+    const double m = __hiloint2double(hi, lo);
+    const double2 tc = __ldg(&kLogTab[(hi >> 13) & 0xFF]);
+    const double r = fma(m, tc.x, -1.0);
+    const double l1p = fma(r * r, horner(kLog1pC, r), r);
+    const double ed = (double)e;
+    return fma(ed, SMCB_LN2_HI, tc.y + fma(ed, SMCB_LN2_LO, l1p));
+}
+#else
 // exp(x): x <= ~709; returns 0 for x < -708 (incl. -inf; the lost range is < 3e-308),
 // +inf for x > 709, NaN for NaN.
 __device__ __forceinline__ double fexp(double x) {
@@ -104,6 +161,7 @@ __device__ __forceinline__ double flog_pos(double x) {
     const double ed = (double)e;
     return fma(ed, SMCB_LN2_HI, fma(s, p, ed * SMCB_LN2_LO));
 }
+#endif  // SMCB_TABLE_MATH
 
 // (sin, cos)(2 pi u) for u in [0, 1)
 __device__ __forceinline__ void fsincos2pi(double u, double &s, double &c) {
