@@ -88,9 +88,10 @@ int smcb_searchsorted(smcb_ctx *ctx, const double *cdf, int64_t n, const double 
 
 /* rs.resampling(scheme, W, M), resampling.py:464-481, 540-627.
  * u_in (device) = the uniforms to use, in the order the reference draws them
- * (systematic 1, stratified m, multinomial m+1, residual m+1); NULL -> Philox.
- * scratch: at least smcb_resample_scratch_doubles(n, m) doubles.
- * su_out / cdf_out may be NULL. */
+ * (systematic 1, stratified m, multinomial m+1, residual m+1, ssp n-1); NULL -> Philox.
+ * scratch: at least smcb_resample_scratch_doubles(n, m) doubles (16-byte aligned).
+ * Asynchronous on the context's stream except SMCB_RS_SSP, which synchronises once to report the
+ * reference's "wrong size for output" ValueError (resampling.py:674-676) as SMCB_EINVAL. */
 int64_t smcb_resample_scratch_doubles(int64_t n, int64_t m);
 int smcb_resample(smcb_ctx *ctx, int scheme, const double *W, int64_t n, int64_t m,
                   int64_t *A_out, const double *u_in, double *scratch);
