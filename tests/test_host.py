@@ -48,24 +48,25 @@ def test_built_for_sm_100a_only():
 
 
 def test_filter_desc_layout_matches_header():
-    """ctypes mirror of smcb_filter_desc: same field order / sizes as the C struct."""
+    """ctypes mirror of smcb_filter_desc: every field at the same offset as in the C struct."""
     from particles_b200 import _lib
-    src = r'''
+    D = _lib.FilterDesc
+    names = [f[0] for f in D._fields_]
+    probes = ", ".join(f"offsetof(smcb_filter_desc, {n})" for n in names)
+    fmt = " ".join(["%zu"] * (len(names) + 1))
+    src = f'''
     #include <stdio.h>
     #include <stddef.h>
     #include "smcb.h"
-    int main(void) { printf("%zu %zu %zu %zu %zu %zu\n", sizeof(smcb_filter_desc),
-        offsetof(smcb_filter_desc, n), offsetof(smcb_filter_desc, params), offsetof(smcb_filter_desc, X),
-        offsetof(smcb_filter_desc, z_in), offsetof(smcb_filter_desc, gathered)); return 0; }
+    int main(void) {{ printf("{fmt}\\n", sizeof(smcb_filter_desc), {probes}); return 0; }}
     '''
     exe = os.path.join(ROOT, "oracle", "_build", "layout_probe")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
                    input=src, text=True, check=True)
     vals = [int(v) for v in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
-    D = _lib.FilterDesc
-    assert vals == [ctypes.sizeof(D), D.n.offset, D.params.offset, D.X.offset, D.z_in.offset,
-                    D.gathered.offset]
+    assert vals[0] == ctypes.sizeof(D)
+    assert dict(zip(names, vals[1:])) == {n: getattr(D, n).offset for n in names}
 
 
 def test_philox_known_answers():
