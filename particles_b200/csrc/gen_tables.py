@@ -3,7 +3,9 @@ of the table-assisted exp / log variants of smcb_math.cuh (SMCB_TABLE_MATH=1).
 
     python particles_b200/csrc/gen_tables.py > particles_b200/csrc/smcb_math_tables.inc
 
-exp:  x = (k / 1024) ln 2 + r,  |r| <= ln2 / 2048,  exp(x) = 2^(k >> 10) * T[k & 1023] * P4(r)
+exp:  x = (k / 1024) ln 2 + r,  |r| <= ln2 / 2048,  exp(x) = 2^(k >> 10) * T[k & 1023] * P4(r)   (SMCB_TABLE_MATH=1)
+      x = (k / 128) ln 2 + r,   |r| <= ln2 / 256,   exp(x) = 2^(k >> 7) * T[k & 127] * P5(r)     (SMCB_TABLE_MATH=2:
+      1 KB table = 8 cache lines, so a divergent lookup touches at most 8 lines)
 log:  m in [sqrt(1/2), sqrt(2)) -> interval j (top mantissa bits), r = m * inv_c[j] - 1, |r| <= 2^-7,
       log(m) = nlog_c[j] + log1p(r),  nlog_c[j] = -log(inv_c[j]) for the ROUNDED inv_c[j]
 """
@@ -47,6 +49,18 @@ print("// T[j] = 2^(j/1024), correctly rounded")
 print("static __device__ const double kExp2Tab[1024] = {")
 for j in range(1024):
     v = float(mp.power(2, mp.mpf(j) / 1024))
+    print(f"    {v!r},")
+print("};")
+
+h = ln2 / 256
+c, _ = fit(mp.exp, -h, h, 5)
+c[0], c[1] = mp.mpf(1), mp.mpf(1)
+e = relerr(mp.exp, c, -h, h)
+emit_poly("kExp5C", c, f"exp(r) on |r| <= ln2/256, degree 5 (c0 = c1 = 1), max rel err {mp.nstr(e, 3)}")
+print("// T[j] = 2^(j/128), correctly rounded")
+print("static __device__ const double kExp2Tab128[128] = {")
+for j in range(128):
+    v = float(mp.power(2, mp.mpf(j) / 128))
     print(f"    {v!r},")
 print("};")
 

@@ -12,8 +12,9 @@
 #endif
 #include "smcb_math_coeffs.inc"
 
-// SMCB_TABLE_MATH=1: table-assisted exp and log (shorter polynomials, one L1-resident table load each):
-//   exp: 1024-entry table of 2^(j/1024) + degree-4 polynomial  (11 -> 4 dependent DFMAs)
+// SMCB_TABLE_MATH=1 / 2: table-assisted exp and log (shorter polynomials, one L1-resident table load each):
+//   exp: 1024-entry table of 2^(j/1024) + degree-4 polynomial  (11 -> 4 dependent DFMAs), or with
+//        SMCB_TABLE_MATH=2 a 128-entry table (8 cache lines) + degree 5
 //   log: 256-entry table of {1/c, -log(1/c)} + degree-6 log1p  (no fp64 division)
 // Same accuracy class (<= ~1.5 ulp, tests/test_math_host.py checks both builds on the CPU).  Off by
 // default until timed on the device against the polynomial-only build (profiles/build_variant.sh).
@@ -68,17 +69,30 @@ __device__ __forceinline__ double horner(const double (&c)[N], double x) {
 #if SMCB_TABLE_MATH
 // exp(x) without range selects: x = (k/1024) ln2 + r, exp(x) = 2^(k >> 10) * T[k & 1023] * P4(r)
 __device__ __forceinline__ double fexp_core(double x) {
-    const double t = fma(x, 1024.0 * SMCB_LOG2E, kRintMagic);
+#if SMCB_TABLE_MATH == 2      // 128-entry table (1 KB: a divergent lookup touches <= 8 L1 lines), degree 5
+    constexpr int kBits = 7;
+#else                         // 1024-entry table (8 KB), degree 4
+    constexpr int kBits = 10;
+#endif
+    constexpr double kScale = (double)(1 << kBits);
+    const double t = fma(x, kScale * SMCB_LOG2E, kRintMagic);
     const double kd = t - kRintMagic;
     const int k = __double2loint(t);                       // |k| < 2^20 for |x| <= 709
-    double r = fma(kd, -(SMCB_LN2_HI / 1024.0), x);        // power-of-two scalings of the split: exact
-    r = fma(kd, -(SMCB_LN2_LO / 1024.0), r);
+    double r = fma(kd, -(SMCB_LN2_HI / kScale), x);        // power-of-two scalings of the split: exact
+    r = fma(kd, -(SMCB_LN2_LO / kScale), r);
+    // exp(r) - 1 = r + r^2 (c2 + c3 r + ...); T + T * (exp(r) - 1) keeps the table value's half ulp
+#if SMCB_TABLE_MATH == 2
+    const double tj = __ldg(&kExp2Tab128[k & 127]);
+    double h = fma(kExp5C[5], r, kExp5C[4]);
+    h = fma(h, r, kExp5C[3]);
+    h = fma(h, r, kExp5C[2]);
+#else
     const double tj = __ldg(&kExp2Tab[k & 1023]);
-    // exp(r) - 1 = r + r^2 (c2 + c3 r + c4 r^2); T + T * (exp(r) - 1) keeps the table value's half ulp
     double h = fma(kExp4C[4], r, kExp4C[3]);
     h = fma(h, r, kExp4C[2]);
+#endif
     const double em1 = fma(r * r, h, r);
-    return fma(tj, em1, tj) * __hiloint2double(((k >> 10) + 1023) << 20, 0);
+    return fma(tj, em1, tj) * __hiloint2double(((k >> kBits) + 1023) << 20, 0);
 }
 __device__ __forceinline__ double fexp(double x) {
     double res = fexp_core(x);

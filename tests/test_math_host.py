@@ -18,7 +18,7 @@ def ulps(got, ref):
     return np.abs(got - ref) / np.spacing(np.abs(ref))
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["polynomial", "table"])
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["polynomial", "table", "small-table"])
 def mh(request):
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, f"libmath_host_{request.param}.so")
