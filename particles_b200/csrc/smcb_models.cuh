@@ -12,7 +12,9 @@
 // `k` carries the per-step scalars (t, y_t, y_{t+1}, host-computed step constants).
 // Parameter layout of smcb_filter_desc.params is documented per model below.
 #pragma once
+#ifndef SMCB_MATH_HOST_TEST      // tests/math_host.cpp compiles this header for the CPU with its own shim
 #include "smcb_common.cuh"
+#endif
 #include "smcb_math.cuh"
 
 namespace smcb {

@@ -13,6 +13,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "oracle", "_build")
 
 
+def build_math_host(table_math):
+    """g++ build of tests/math_host.cpp (device math + model headers compiled for the host)."""
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, f"libmath_host_{table_math}.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
+                           f"-DSMCB_TABLE_MATH={table_math}", "-I", os.path.join(ROOT, "particles_b200", "csrc"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "math_host.cpp"), "-o", so])
+    return C.CDLL(so)
+
+
 def ulps(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     return np.abs(got - ref) / np.spacing(np.abs(ref))
@@ -20,12 +30,7 @@ def ulps(got, ref):
 
 @pytest.fixture(scope="module", params=[0, 1, 2], ids=["polynomial", "table", "small-table"])
 def mh(request):
-    os.makedirs(BUILD, exist_ok=True)
-    so = os.path.join(BUILD, f"libmath_host_{request.param}.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-DSMCB_TABLE_MATH={request.param}",
-                           "-I", os.path.join(ROOT, "particles_b200", "csrc"), os.path.join(ROOT, "tests", "math_host.cpp"),
-                           "-o", so])
-    lib = C.CDLL(so)
+    lib = build_math_host(request.param)
     assert lib.mh_table_math() == request.param
     return lib
 
