@@ -251,6 +251,14 @@ int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *out8);
  * [5]=log_mean_w, [6]=max lw, [7]=sum w */
 int smcb_filter_state(smcb_filter *f, double *out8);
 
+/* ---------------------------------------------------------------------------
+ * measured ceilings of this device (bench.py "roofline.secondary"; no reference counterpart)
+ * ------------------------------------------------------------------------- */
+/* fp64 FMA issue peak: out3 = {TFLOP/s, DFMA warp-instructions / cycle / SM at sm_mhz (0: skip), ms} */
+int smcb_measure_fp64_peak(smcb_ctx *ctx, double sm_mhz, double *out3_host);
+/* read + write streaming probe with 16-byte accesses over n doubles (n even): out1 = {GB/s} */
+int smcb_measure_stream_peak(smcb_ctx *ctx, const double *in, double *out, int64_t n, double *out1_host);
+
 #ifdef __cplusplus
 }
 #endif

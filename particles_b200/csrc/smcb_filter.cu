@@ -333,3 +333,12 @@ extern "C" int smcb_p2p_free(void *dev_ptr) {
     if (dev_ptr) SMCB_CUDA(cudaFree(dev_ptr));
     return SMCB_OK;
 }
+
+#ifdef SMCB_TRACE
+// debug builds only (profiles/build_variant.sh trace -DSMCB_TRACE): timeline of the last step-kernel launch
+extern "C" int smcb_debug_trace(unsigned long long *host_out, int n_words) {
+    SMCB_CUDA(cudaDeviceSynchronize());
+    SMCB_CUDA(cudaMemcpyFromSymbol(host_out, smcb::g_trace, sizeof(unsigned long long) * n_words));
+    return SMCB_OK;
+}
+#endif

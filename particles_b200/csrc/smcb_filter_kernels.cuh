@@ -583,8 +583,25 @@ static __global__ void __launch_bounds__(kBlock) k_scan_spacings(FilterArgs a) {
 // MODE 0: both branches, chosen at run time from FilterDev.rs_flag.  MODE 1 / 2 compile the identity /
 // resampling branch alone (own register allocation); measured no faster than MODE 0 (DESIGN.md
 // section 6), so only MODE 0 is instantiated.
+#ifdef SMCB_TRACE
+// per-CTA timeline of the LAST launch of the step kernel: {start, main loop done, exit, smid} in ns
+__device__ unsigned long long g_trace[4 * 2048];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+}
+#endif
 template <class M, int FK, int SCHEME, int MODE = 0>
 __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M model, FilterArgs a) {
+#ifdef SMCB_TRACE
+    if (threadIdx.x == 0) { g_trace[4 * blockIdx.x] = gtimer(); g_trace[4 * blockIdx.x + 3] = smid(); }
+#endif
     constexpr bool APF = FkTraits<FK>::apf;
     constexpr int K = APF ? 2 : 1;
     constexpr int kStage = (MODE == 1) ? 2 : 2048;     // doubles of CDF staged per output tile
@@ -844,6 +861,15 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_move(M 
     }
 
     Lse3 tot[K];
+#ifdef SMCB_TRACE
+    if (threadIdx.x == 0) g_trace[4 * blockIdx.x + 1] = gtimer();
+    const bool last_ = grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot);
+    if (!last_) { if (threadIdx.x == 0) g_trace[4 * blockIdx.x + 2] = gtimer(); return; }
+    finalize_step<APF>(a, tot[0], tot[K - 1], tot[0], tot[K - 1]);
+    __syncthreads();
+    if (threadIdx.x == 0) g_trace[4 * blockIdx.x + 2] = gtimer();
+    return;
+#endif
     if (!grid_merge_lse3<kBlock, K>(acc, a.partials, a.ticket, smem, tot)) return;
     if (a.world > 1) { publish_local<K>(a, tot); return; }
     finalize_step<APF>(a, tot[0], tot[K - 1], tot[0], tot[K - 1]);

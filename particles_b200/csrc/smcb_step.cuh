@@ -1,0 +1,1367 @@
+#pragma once
+// smcb_step.cuh -- the fused SMC step (particles/core.py:369-383): ONE kernel launch per step.
+//
+//   k_step(t), every CTA:
+//     prologue   merge the per-CTA partials (max, sum exp, sum exp^2 [, sum w x, sum w x^2]) that step
+//                t-1 left behind -- every CTA does it redundantly, in the same fixed order, so all of
+//                them hold identical bits -- [sharded: exchange the shard totals through the NVLink
+//                mailboxes], then compute_summaries of step t-1 (core.py:351-367) and the ESS test of
+//                step t (core.py:181-183).  CTA 0 records the (T, 4) summary row, the moments row and the
+//                state S_{t-1}.  No "last CTA" serial tail, no separate finish kernel.
+//     no resampling:  xp = X_k -> x' ~ M_t(xp) -> lw' = lw + logG -> partials            32 B/particle
+//     resampling:     W_i = exp(lw_i - m)/s -> CDF of the CTA's own range (16 B/particle)
+//                     -> grid barrier -> su_k -> A_k = search(cdf) -> xp = X[A_k] -> x' -> lw' = logG
+//                     -> partials                                                         40 B/particle
+//   k_tail(t)  (one CTA, once per enqueued batch): the prologue alone, so that the summaries of the last
+//              enqueued step exist before the host reads them.  Idempotent with the next k_step.
+//
+// The step index is a kernel argument (the host mirrors it); everything else a step needs from its
+// predecessor is in the partials (double-buffered by step parity) and in S_{t-2}.
+#include <cooperative_groups.h>
+#include <string.h>
+
+#include <new>
+
+#include "smcb_common.cuh"
+#include "smcb_math.cuh"
+#include "smcb_models.cuh"
+#include "smcb_scan.cuh"
+#include "smcb_search.cuh"
+
+using namespace smcb;
+
+namespace smcb {
+
+constexpr int kPartStride = 16;     // doubles per CTA partial row: w(m,s,q,-) aux(m,s,q,-) sx[4] sxx[4]
+constexpr int kMailStride = 32;     // doubles per mailbox slot: the 16 above, then epochs
+constexpr int kMailEpoch = 16;      // slot[16] = t + 1 once the sender's statistics of step t are complete
+constexpr int kMailScan = 17;       // slot[17] = t + 1 once the sender's CDF of (resampling) step t is complete
+constexpr int kPer = (kMaxGrid + kBlock - 1) / kBlock;   // partial rows per thread in the prologue
+constexpr int kMaxD = 4;
+
+// S_t: what is known once step t is finalised; st[t & 1]
+struct StepState {
+    double logLt, log_mean_w, ess;
+    double wm, ws, wq;      // (max, sum exp, sum exp^2) of the inferential weights over ALL particles
+    long long t;            // the step this record belongs to
+    long long nrs;          // resampling steps among steps 1..t   (grid-barrier epochs)
+    int rs;                 // step t resampled
+    int rs_next;            // decision for step t + 1
+    int pad[2];
+};
+
+struct FilterArgs {
+    double *X[2];
+    double *lw[2];
+    long long *A;
+    double *cdf;
+    double *su;              // multinomial: z = cumsum(-log u), (n + 1)
+    const double *data;      // (T, dy)
+    const double *sc;        // (T) per-step model constants or NULL
+    double *summaries;       // (T, 4)
+    double *moments;         // NULL or (T, 2 D): weighted mean and variance per component (collectors.Moments)
+    const double *z_in, *u_in;
+    StepState *st;           // [2]
+    int *sync_timeout;       // a bounded wait expired (diagnostic; results are then invalid)
+    double *partials;        // [2][kMaxGrid][kPartStride]
+    unsigned long long *bar; // grid-barrier arrivals, never reset
+    double *blk_agg;         // multinomial: per-CTA sums of the exponential spacings (grid + 1)
+    int64_t n, n_global, index_offset, T;
+    int dy;
+    int world, rank;
+    int grid;
+    int64_t chunk;           // pairs of particles per block (blocked assignment, multiple of kBlock)
+    double essrmin;
+    Philox key;
+    // sharded filters: host-driven exchange (NCCL all-gather of local_stats into gathered) ...
+    double *local_stats;     // this rank's 16 statistics
+    const double *gathered;  // world x 16, rank-major
+    // ... or the peer mailboxes: [parity][sender][kMailStride]; mail_peer[p] = rank p's mailbox mapped here
+    double *mail_local;
+    double *mail_peer[8];
+    // exact global resampling: peers' particles and CDFs mapped over NVLink
+    int rs_global;
+    const double *pX[8][2];
+    const double *pcdf[8];
+};
+
+__device__ __forceinline__ void wait_epoch(const volatile double *flag, double epoch, int *timeout) {
+    const long long t0 = clock64();
+    if (*reinterpret_cast<volatile int *>(timeout)) return;   // already broken: do not stall again
+    while (*flag < epoch) {
+        if (clock64() - t0 > 8000000000ll) { *timeout = 1; break; }    // ~4 s at 2 GHz
+    }
+    __threadfence_system();
+}
+
+__device__ __forceinline__ StepK step_consts(const FilterArgs &a, long long t) {
+    StepK k;
+    k.t = t;
+#pragma unroll
+    for (int i = 0; i < kMaxDy; i++) {
+        k.yv[i] = (i < a.dy && t >= 0) ? a.data[t * a.dy + i] : 0.0;
+        k.yn[i] = (i < a.dy && t + 1 < a.T) ? a.data[(t + 1) * a.dy + i] : 0.0;
+    }
+    k.y = k.yv[0];
+    k.y_next = k.yn[0];
+    k.sc0 = (a.sc && t >= 0) ? a.sc[t] : 0.0;
+    return k;
+}
+
+__device__ __forceinline__ double fix_nan(double v) { return v != v ? -CUDART_INF : v; }  // resampling.py:220
+
+// Weights.__init__ scalars from the merged triple (resampling.py:217-226):
+//   log_mean = m + log(s / N);  ESS = 1 / sum (w/s)^2 = s^2 / q
+// All -inf (m == -inf) or any +inf (m == +inf) give NaN everywhere, as NumPy does.
+__device__ __forceinline__ void weights_scalars(const Lse3 &a, double n, double &log_mean, double &ess) {
+    if (a.m == -CUDART_INF || a.m == CUDART_INF || a.m != a.m) {
+        log_mean = CUDART_NAN;
+        ess = CUDART_NAN;
+        return;
+    }
+    log_mean = a.m + log(a.s / n);
+    ess = (a.s * a.s) / a.q;
+}
+
+// exp(m - M) for m <= M, 0 for an empty accumulator; NaN when both are +inf (NumPy's inf - inf)
+__device__ __forceinline__ double shift_factor(double m, double M) {
+    return (m == -CUDART_INF) ? 0.0 : fexp_neg(m - M);
+}
+
+// ---------------------------------------------------------------------------
+// block-wide fixed-order reductions; every thread receives the result
+// ---------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (kBlock/32) x NV */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+#pragma unroll
+        for (int mask = 16; mask > 0; mask >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, v[j], mask);
+            v[j] = (o > v[j] || o != o) ? o : v[j];          // NaN wins (np.max of a NaN array is NaN)
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) smem[warp * NV + j] = v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        double m = smem[j];
+#pragma unroll
+        for (int w = 1; w < kBlock / 32; w++) {
+            const double o = smem[w * NV + j];
+            m = (o > m || o != o) ? o : m;
+        }
+        v[j] = m;
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem /* (kBlock/32) x NV */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+#pragma unroll
+        for (int mask = 16; mask > 0; mask >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], mask);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) smem[warp * NV + j] = v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        double s = smem[j];
+#pragma unroll
+        for (int w = 1; w < kBlock / 32; w++) s += smem[w * NV + j];
+        v[j] = s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// per-thread accumulators: (max, sum exp, sum exp^2) of the log-weights with ONE exp per value (the
+// running shift only moves when a batch maximum exceeds it) and, optionally, sum w x / sum w x^2 per
+// component for collectors.Moments (resampling.py:320-338) relative to the same shift.
+// Values equal to -inf (masked slots) contribute exactly 0.
+// ---------------------------------------------------------------------------
+template <int D>
+struct Acc {
+    Lse3 w;
+    double sx[D], sxx[D];
+};
+
+template <int D>
+__device__ __forceinline__ void acc_init(Acc<D> &a) {
+    a.w = lse3_empty();
+#pragma unroll
+    for (int c = 0; c < D; c++) { a.sx[c] = 0.0; a.sxx[c] = 0.0; }
+}
+
+template <int NV, int D>
+__device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], const double (&x)[NV][D], bool mom) {
+    double mb = v[0];
+#pragma unroll
+    for (int j = 1; j < NV; j++) mb = fmax(mb, v[j]);
+    if (mb > a.w.m) {                       // also the first time (m = -inf): fexp(-inf) = 0
+        const double r = fexp_neg(a.w.m - mb);
+        a.w.s *= r;
+        a.w.q *= r * r;
+        if (mom) {
+#pragma unroll
+            for (int c = 0; c < D; c++) { a.sx[c] *= r; a.sxx[c] *= r; }
+        }
+        a.w.m = mb;
+    }
+    if (a.w.m == -CUDART_INF) return;       // nothing but -inf so far
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const double e = fexp_neg(v[j] - a.w.m);
+        a.w.s += e;
+        a.w.q = fma(e, e, a.w.q);
+        if (mom && v[j] != -CUDART_INF) {
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+                const double ex = e * x[j][c];
+                a.sx[c] += ex;
+                a.sxx[c] = fma(ex, x[j][c], a.sxx[c]);
+            }
+        }
+    }
+}
+
+struct StepSmem {
+    double red[(kBlock / 32) * 16];
+    double peer[8][kMailStride];
+    double goff[9], gpi[8];
+    double pref[2];
+};
+
+// this CTA's row of the partials of step t: block reduction of the thread accumulators
+template <int D, bool APF>
+__device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, const Acc<D> &acc, const Lse3 &aux,
+                                              bool mom, StepSmem &sh) {
+    double mx[2] = {acc.w.m, APF ? aux.m : -CUDART_INF};
+    block_max_all<2>(mx, sh.red);
+    const double ew = shift_factor(acc.w.m, mx[0]);
+    const double ea = APF ? shift_factor(aux.m, mx[1]) : 0.0;
+    double v[4 + 2 * D];
+    v[0] = acc.w.s * ew;
+    v[1] = acc.w.q * (ew * ew);
+    v[2] = APF ? aux.s * ea : 0.0;
+    v[3] = APF ? aux.q * (ea * ea) : 0.0;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        v[4 + c] = mom ? acc.sx[c] * ew : 0.0;
+        v[4 + D + c] = mom ? acc.sxx[c] * ew : 0.0;
+    }
+    block_sum_all<4 + 2 * D>(v, sh.red);
+    if (threadIdx.x == 0) {
+        double *p = a.partials + ((size_t)(t & 1) * kMaxGrid + blockIdx.x) * kPartStride;
+        p[0] = mx[0]; p[1] = v[0]; p[2] = v[1]; p[3] = 0.0;
+        p[4] = APF ? mx[1] : mx[0]; p[5] = APF ? v[2] : v[0]; p[6] = APF ? v[3] : v[1]; p[7] = 0.0;
+#pragma unroll
+        for (int c = 0; c < kMaxD; c++) {
+            p[8 + c] = (c < D) ? v[4 + (c < D ? c : 0)] : 0.0;
+            p[12 + c] = (c < D) ? v[4 + D + (c < D ? c : 0)] : 0.0;
+        }
+    }
+}
+
+// merge in a fixed order (a then b); same algebra as Weights.__init__ on the concatenation
+__device__ __forceinline__ void merge16(double (&a)[16], const double *b) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {           // k = 0: inferential triple (+ moments), k = 1: auxiliary triple
+        const double am = a[4 * k], bm = b[4 * k];
+        const double M = (bm > am || bm != bm) ? bm : am;
+        const double ea = shift_factor(am, M), eb = shift_factor(bm, M);
+        a[4 * k] = M;
+        a[4 * k + 1] = a[4 * k + 1] * ea + b[4 * k + 1] * eb;
+        a[4 * k + 2] = a[4 * k + 2] * (ea * ea) + b[4 * k + 2] * (eb * eb);
+        if (k == 0) {
+#pragma unroll
+            for (int c = 8; c < 16; c++) a[c] = a[c] * ea + b[c] * eb;
+        }
+    }
+}
+
+struct StepDecision {
+    int rs;                   // resample at step t
+    long long nrs_prev;       // resampling steps before step t (grid-barrier epochs already passed)
+    double reset_c;           // log-weight every resampled particle restarts from (minus logeta[A] for an APF)
+    double xm, xs;            // (max, sum exp) of this shard's (auxiliary) weights: the CDF's normalisation
+    double p_b, p_next;       // this CTA's range of the CDF
+};
+
+// compute_summaries of step s = t - 1 (core.py:351-367) + time_to_resample of step t (core.py:181-183),
+// by every CTA; `writer` CTAs also record S_s, the summary row and the moments row.
+template <bool APF>
+__device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
+                                                      bool need_prefix) {
+    const long long s = t - 1;
+    const int G = a.grid, tid = threadIdx.x;
+    const double *part = a.partials + (size_t)(s & 1) * kMaxGrid * kPartStride;
+    const int b0 = tid * kPer;
+    const bool mom = writer && (a.moments != nullptr || a.world > 1);
+    // rows b0 .. b0 + kPer - 1 of the partials (contiguous per thread: the prefix below needs that)
+    double pm[kPer], ps[kPer], pq[kPer], xm_[kPer], xs_[kPer], xq_[kPer];
+    double mx[2] = {-CUDART_INF, -CUDART_INF};
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const int b = b0 + i;
+        pm[i] = -CUDART_INF; ps[i] = 0.0; pq[i] = 0.0; xm_[i] = -CUDART_INF; xs_[i] = 0.0; xq_[i] = 0.0;
+        if (b < G) {
+            const double4 r0 = __ldcg(reinterpret_cast<const double4 *>(part + (size_t)b * kPartStride));
+            pm[i] = r0.x; ps[i] = r0.y; pq[i] = r0.z;
+            if (APF) {
+                const double4 r1 = __ldcg(reinterpret_cast<const double4 *>(part + (size_t)b * kPartStride + 4));
+                xm_[i] = r1.x; xs_[i] = r1.y; xq_[i] = r1.z;
+            } else {
+                xm_[i] = pm[i]; xs_[i] = ps[i]; xq_[i] = pq[i];
+            }
+            mx[0] = (pm[i] > mx[0] || pm[i] != pm[i]) ? pm[i] : mx[0];
+            mx[1] = (xm_[i] > mx[1] || xm_[i] != xm_[i]) ? xm_[i] : mx[1];
+        }
+    }
+    block_max_all<2>(mx, sh.red);
+    double loc[16];                                   // this shard's statistics, mailbox layout
+    {
+        double v[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) v[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const int b = b0 + i;
+            if (b < G) {
+                const double ew = shift_factor(pm[i], mx[0]);
+                v[0] += ps[i] * ew;
+                v[1] += pq[i] * (ew * ew);
+                if (APF) {
+                    const double ea = shift_factor(xm_[i], mx[1]);
+                    v[2] += xs_[i] * ea;
+                    v[3] += xq_[i] * (ea * ea);
+                }
+                if (mom) {
+                    const double *r = part + (size_t)b * kPartStride + 8;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[4 + c] += __ldcg(r + c) * ew;
+                }
+            }
+        }
+        block_sum_all<12>(v, sh.red);
+        loc[0] = mx[0]; loc[1] = v[0]; loc[2] = v[1]; loc[3] = 0.0;
+        loc[4] = APF ? mx[1] : mx[0]; loc[5] = APF ? v[2] : v[0]; loc[6] = APF ? v[3] : v[1]; loc[7] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) loc[8 + c] = v[4 + c];
+    }
+    double glob[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) glob[j] = loc[j];
+    if (a.world > 1) {
+        const double *gath = a.gathered;
+        int gstride = 16;
+        if (a.mail_local != nullptr) {
+            // fused exchange over NVLink peer memory: CTA 0 stores this shard's statistics of step s into every
+            // peer's mailbox (one lane per peer), fences, raises the epoch; every CTA waits for `world` epochs
+            if (writer && tid < a.world) {
+                double *slot = a.mail_peer[tid] + ((size_t)(s & 1) * a.world + a.rank) * kMailStride;
+#pragma unroll
+                for (int i = 0; i < 16; i++) slot[i] = loc[i];
+                __threadfence_system();
+                *reinterpret_cast<volatile double *>(slot + kMailEpoch) = (double)(s + 1);
+            }
+            const double *box = a.mail_local + (size_t)(s & 1) * a.world * kMailStride;
+            if (tid < a.world) {
+                wait_epoch(box + (size_t)tid * kMailStride + kMailEpoch, (double)(s + 1), a.sync_timeout);
+                for (int i = 0; i < 16; i++)
+                    sh.peer[tid][i] = *reinterpret_cast<const volatile double *>(box + (size_t)tid * kMailStride + i);
+            }
+            __syncthreads();
+        } else {
+            if (tid < a.world)
+                for (int i = 0; i < 16; i++) sh.peer[tid][i] = __ldcg(gath + (size_t)tid * gstride + i);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) glob[j] = sh.peer[0][j];
+        for (int r = 1; r < a.world; r++) merge16(glob, sh.peer[r]);         // rank order: identical bits everywhere
+        if (a.rs_global && tid == 0) {
+            // shard r's share of the global (auxiliary) weight mass, rank order
+            double run = 0.0;
+            for (int r = 0; r < a.world; r++) {
+                const double pm_ = sh.peer[r][4], ps_ = sh.peer[r][5];
+                const double pi = (pm_ == -CUDART_INF) ? 0.0 : ps_ * fexp_neg(pm_ - glob[4]) / glob[5];
+                sh.goff[r] = run;
+                sh.gpi[r] = pi;
+                run = run + pi;
+            }
+            sh.goff[a.world] = run;
+        }
+        __syncthreads();
+    }
+    const Lse3 w{glob[0], glob[1], glob[2]}, x{glob[4], glob[5], glob[6]};
+    const Lse3 xl{loc[4], loc[5], loc[6]};
+    const StepState prev = (s >= 1) ? a.st[(s - 1) & 1] : StepState{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1, 0, 0, 0, {0, 0}};
+    const double N = (double)a.n_global;
+    double log_mean, ess, lm_aux, ess_aux;
+    weights_scalars(w, N, log_mean, ess);
+    weights_scalars(x, N, lm_aux, ess_aux);
+    const int rs_s = prev.rs_next;                                          // did step s resample?
+    const bool fresh = (s == 0) || (rs_s != 0);
+    const double loglt = fresh ? log_mean : (log_mean - prev.log_mean_w);   // core.py:355-358
+    const double logLt = prev.logLt + loglt;
+    StepDecision d;
+    d.rs = (s + 1 < a.T) && (ess_aux < N * a.essrmin);                      // strict <, NaN -> False
+    d.nrs_prev = prev.nrs + (rs_s ? 1 : 0);
+    // log-weight every resampled particle restarts from (minus logeta[A] for an APF):
+    //   single device, non-APF : 0                        (Weights(), core.py:305)
+    //   single device, APF     : log_mean_exp(logetat, W) (core.py:302) = LSE(aux) - LSE(w)
+    //   sharded, per shard     : LSE_shard(aux) - LSE_all(w) + log(world): each shard resamples locally and
+    //                            carries its share of the mass
+    //   sharded, global        : the reference's restart from the global sums
+    double rc = 0.0;
+    if (a.rs_global) rc = APF ? (log(x.s) + x.m) - (log(w.s) + w.m) : 0.0;
+    else if (APF || a.world > 1) rc = (log(xl.s) + xl.m) - (log(w.s) + w.m) + log((double)a.world);
+    d.reset_c = rc;
+    d.xm = xl.m; d.xs = xl.s;
+    d.p_b = 0.0; d.p_next = 0.0;
+    if (writer && tid == 0) {
+        double *row = a.summaries + (size_t)s * SMCB_SUMMARY_STRIDE;
+        row[0] = ess; row[1] = logLt; row[2] = (double)rs_s; row[3] = log_mean;
+        StepState *o = a.st + (s & 1);
+        o->logLt = logLt; o->log_mean_w = log_mean; o->ess = ess;
+        o->wm = w.m; o->ws = w.s; o->wq = w.q;
+        o->t = s; o->nrs = d.nrs_prev; o->rs = rs_s; o->rs_next = d.rs;
+        if (a.moments != nullptr) {                                        // wmean_and_var, resampling.py:320-338
+            double *mrow = a.moments + (size_t)s * 2 * kMaxD;
+#pragma unroll
+            for (int c = 0; c < kMaxD; c++) {
+                const double mean = glob[8 + c] / w.s;
+                mrow[c] = mean;
+                mrow[kMaxD + c] = glob[12 + c] / w.s - mean * mean;
+            }
+        }
+    }
+    if (d.rs && need_prefix) {
+        // The CTAs own contiguous particle ranges, so their partial sums ARE the tile aggregates of the
+        // weight scan: exclusive prefixes P_0 = 0 <= P_1 <= ... <= P_G (fixed order, monotone, the same bits
+        // in every CTA), and the scan needs no look-back at all.
+        double run = 0.0, lc[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const int b = b0 + i;
+            double v = 0.0;
+            if (b < G) v = xs_[i] * shift_factor(xm_[i], d.xm) / d.xs;
+            run = run + v;
+            lc[i] = run;
+        }
+        const int lane = tid & 31, warp = tid >> 5;
+        const double iw = warp_scan_monotone(run, lane);
+        if (lane == 31) sh.red[warp] = iw;
+        __syncthreads();
+        double woff = 0.0;
+        for (int w_ = 0; w_ < kBlock / 32; w_++)
+            if (w_ < warp) woff = woff + sh.red[w_];
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double cap = woff + iw;
+        if (tid == 0 && blockIdx.x == 0) sh.pref[0] = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPer; i++) {
+            const int b = b0 + i;                       // row b gives P_{b+1}
+            if (b < G) {
+                const double p = fmin(excl + lc[i], cap);
+                if (b + 1 == (int)blockIdx.x) sh.pref[0] = p;
+                if (b == (int)blockIdx.x) sh.pref[1] = p;
+            }
+        }
+        __syncthreads();
+        d.p_b = sh.pref[0];
+        d.p_next = sh.pref[1];
+        __syncthreads();
+    }
+    return d;
+}
+
+// all CTAs of the (co-resident, cooperative) grid have arrived `epoch` times
+__device__ __forceinline__ void grid_barrier(const FilterArgs &a, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        atomicAdd(a.bar, 1ull);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned long long *>(a.bar) < target) {
+            if (clock64() - t0 > 8000000000ll) { *a.sync_timeout = 2; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// t = 0: generate_particles + reweight (core.py:315-324, 373-374)
+// ---------------------------------------------------------------------------
+template <class M, int FK>
+__global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
+    constexpr bool APF = FkTraits<FK>::apf;
+    constexpr int D = M::D, NZ = M::NZ;
+    __shared__ StepSmem sh;
+    const StepK k = step_consts(a, 0);
+    double *Xo = a.X[0], *lwo = a.lw[0];
+    Acc<D> acc;
+    acc_init(acc);
+    Lse3 aux = lse3_empty();
+    const bool mom = a.moments != nullptr || a.world > 1;
+    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const bool has_next = APF && a.T > 1;
+    const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
+    const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+    for (int64_t p = pstart + threadIdx.x; p < pend; p += kBlock) {
+        double z[2][NZ], x[2][D], l[2], av[2];
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            if (a.z_in) {                                  // injected normals: (T, NZ, n)
+                const double *zz = a.z_in + (size_t)c * n;
+                z[0][c] = zz[2 * p];
+                z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
+            } else {
+                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, (uint32_t)c, z[0][c], z[1][c]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double d;
+            model_init<M, FK>(model, k, z[j], x[j], d);
+            l[j] = fix_nan(d);
+            av[j] = has_next ? fix_nan(l[j] + model_logeta<M>(model, k, x[j])) : -CUDART_INF;
+        }
+        if (2 * p + 1 < n) {
+            if ((n & 1) == 0 || D == 1) {
+#pragma unroll
+                for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
+            } else {                                      // odd SoA stride: component rows are only 8-byte aligned
+#pragma unroll
+                for (int c = 0; c < D; c++) { Xo[(size_t)c * n + 2 * p] = x[0][c]; Xo[(size_t)c * n + 2 * p + 1] = x[1][c]; }
+            }
+            st2(lwo + 2 * p, l[0], l[1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) Xo[(size_t)c * n + 2 * p] = x[0][c];
+            lwo[2 * p] = l[0];
+            l[1] = -CUDART_INF; av[1] = -CUDART_INF;   // masked slot contributes exactly 0
+        }
+        acc_add_batch<2, D>(acc, l, x, mom);
+        if (APF) lse3_add_batch<2>(aux, av);
+    }
+    write_partial<D, APF>(a, 0, acc, aux, mom, sh);
+}
+
+// ---------------------------------------------------------------------------
+// resampling steps: normalised (auxiliary) weights -> CDF   (resampling.py:223-225 + scan)
+// ---------------------------------------------------------------------------
+template <class M, int FK>
+struct LoadWeights {
+    const double *lw, *X;
+    int64_t ntot;  // particles on this device (SoA component stride)
+    double m, s;
+    M model;
+    StepK kprev;   // step t-1 with y_next = data[t]: what logeta(t-1, X) needs
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+        constexpr bool APF = FkTraits<FK>::apf;
+        constexpr int D = M::D;
+        double l[8], x[8][APF ? D : 1];
+        const bool vec_x = (D == 1) || ((ntot & 1) == 0);
+        if (i0 + 8 <= n) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { double2 t = ld2(lw + i0 + j); l[j] = t.x; l[j + 1] = t.y; }
+            if (APF) {
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        if (vec_x) {
+                            double2 t = ld2(X + (size_t)c * ntot + i0 + j);
+                            x[j][APF ? c : 0] = t.x; x[j + 1][APF ? c : 0] = t.y;
+                        } else {
+                            x[j][APF ? c : 0] = X[(size_t)c * ntot + i0 + j];
+                            x[j + 1][APF ? c : 0] = X[(size_t)c * ntot + i0 + j + 1];
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                l[j] = (i0 + j < n) ? lw[i0 + j] : -CUDART_INF;
+                if (APF) {
+#pragma unroll
+                    for (int c = 0; c < D; c++) x[j][APF ? c : 0] = (i0 + j < n) ? X[(size_t)c * ntot + i0 + j] : 0.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            double e = l[j];
+            if (APF) e = fix_nan(e + model_logeta<M>(model, kprev, x[j]));
+            v[j] = (i0 + j < n) ? fexp(e - m) / s : 0.0;
+        }
+    }
+};
+
+// this CTA scans the particles it owns, [2 b chunk, 2 (b+1) chunk), from the exclusive prefix P_b the
+// prologue derived from the previous step's partial sums; every value is clamped into [P_b, P_{b+1}], so the
+// CDF is non-decreasing across CTAs by construction
+template <class M, int FK>
+__device__ __forceinline__ void scan_own_range(const M &model, const FilterArgs &a, long long t, int cur,
+                                               const StepDecision &d, double *s_warp) {
+    LoadWeights<M, FK> load;
+    load.lw = a.lw[cur];
+    load.X = a.X[cur];
+    load.ntot = a.n;
+    load.m = d.xm;
+    load.s = d.xs;
+    load.model = model;
+    load.kprev = step_consts(a, t - 1);
+    const int64_t n = a.n;
+    const int64_t e0 = 2 * (int64_t)blockIdx.x * a.chunk;
+    const int64_t e1 = e0 + 2 * a.chunk < n ? e0 + 2 * a.chunk : n;
+    const double p_b = d.p_b, p_next = d.p_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double carry = 0.0;
+    for (int64_t base0 = e0; base0 < e1; base0 += kScanTile) {
+        const int64_t i0 = base0 + (int64_t)tid * kScanItems;
+        double r[kScanItems];
+        load(i0, e1, r);
+#pragma unroll
+        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
+        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
+        if (lane == 31) s_warp[warp] = iw;
+        __syncthreads();
+        double woff = 0.0, total = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) {
+            if (w < warp) woff = woff + s_warp[w];
+            total = total + s_warp[w];
+        }
+        const double incl = woff + iw;
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double b_i = p_b + carry;                       // base of this sub-tile
+        const double carry_next = carry + total;
+        const double b_next = fmin(p_b + carry_next, p_next); // base of the next one
+        const double tb = b_i + excl;
+        const double cap = fmin(b_i + incl, b_next);
+        double o[kScanItems];
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) o[j] = fmin(tb + r[j], cap);
+        if (i0 + kScanItems <= e1) {
+            store_items(a.cdf, i0, o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++)
+                if (i0 + j < e1) a.cdf[i0 + j] = o[j];
+        }
+        carry = carry_next;
+        __syncthreads();
+    }
+}
+
+// multinomial: exponential spacings z = cumsum(-log u), n + 1 of them (resampling.py:536-537), blocked like
+// the weights: pass 1 leaves v_i = -log u_i in su[] and the CTA's sum in blk_agg[]; after a grid barrier
+// pass 2 scans the CTA's range from the (fixed-order, monotone) prefix of the CTA sums.
+__device__ __forceinline__ void spacings_range(const FilterArgs &a, int64_t &e0, int64_t &e1) {
+    const int64_t n1 = a.n + 1;
+    e0 = 2 * (int64_t)blockIdx.x * a.chunk;
+    e1 = e0 + 2 * a.chunk;
+    if (blockIdx.x == gridDim.x - 1 || e1 > n1) e1 = n1;          // the last CTA also takes element n
+    if (e0 > n1) e0 = n1;
+}
+
+__device__ __forceinline__ void spacings_pass1(const FilterArgs &a, long long t, StepSmem &sh) {
+    int64_t e0, e1;
+    spacings_range(a, e0, e1);
+    const double *uin = a.u_in ? a.u_in + (size_t)t * (a.n + 1) : nullptr;
+    double acc[1] = {0.0};
+    for (int64_t i = e0 + 2 * (int64_t)threadIdx.x; i < e1; i += 2 * kBlock) {
+        double u0, u1;
+        if (uin) { u0 = uin[i]; u1 = (i + 1 < e1) ? uin[i + 1] : 1.0; }
+        else uniform_pair(a.key, (uint64_t)(i >> 1), (uint32_t)t, kPurposeUniform, u0, u1);
+        const double v0 = -log(u0);                    // u may be 0 or injected: library log
+        const double v1 = (i + 1 < e1) ? -log(u1) : 0.0;
+        a.su[i] = v0;
+        if (i + 1 < e1) a.su[i + 1] = v1;
+        acc[0] += v0 + v1;
+    }
+    block_sum_all<1>(acc, sh.red);
+    if (threadIdx.x == 0) a.blk_agg[blockIdx.x] = acc[0];
+}
+
+__device__ __forceinline__ void spacings_pass2(const FilterArgs &a, StepSmem &sh, double *s_warp) {
+    // prefix of the CTA sums: every CTA runs the same sequential-per-thread + monotone block scan
+    const int G = a.grid, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = tid * kPer;
+    double run = 0.0, lc[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const int b = b0 + i;
+        const double v = (b < G) ? __ldcg(a.blk_agg + b) : 0.0;
+        run = run + v;
+        lc[i] = run;
+    }
+    const double iw0 = warp_scan_monotone(run, lane);
+    if (lane == 31) sh.red[warp] = iw0;
+    __syncthreads();
+    double woff0 = 0.0;
+    for (int w_ = 0; w_ < kBlock / 32; w_++)
+        if (w_ < warp) woff0 = woff0 + sh.red[w_];
+    const double up0 = __shfl_up_sync(0xffffffffu, iw0, 1);
+    const double excl0 = (lane == 0) ? woff0 : (woff0 + up0);
+    const double cap0 = woff0 + iw0;
+    if (tid == 0 && blockIdx.x == 0) sh.pref[0] = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const int b = b0 + i;
+        if (b < G) {
+            const double p = fmin(excl0 + lc[i], cap0);
+            if (b + 1 == (int)blockIdx.x) sh.pref[0] = p;
+            if (b == (int)blockIdx.x) sh.pref[1] = p;
+        }
+    }
+    __syncthreads();
+    const double p_b = sh.pref[0], p_next = sh.pref[1];
+    __syncthreads();
+    int64_t e0, e1;
+    spacings_range(a, e0, e1);
+    double carry = 0.0;
+    for (int64_t base0 = e0; base0 < e1; base0 += kScanTile) {
+        const int64_t i0 = base0 + (int64_t)tid * kScanItems;
+        double r[kScanItems];
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) r[j] = (i0 + j < e1) ? a.su[i0 + j] : 0.0;
+#pragma unroll
+        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
+        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
+        if (lane == 31) s_warp[warp] = iw;
+        __syncthreads();
+        double woff = 0.0, total = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) {
+            if (w < warp) woff = woff + s_warp[w];
+            total = total + s_warp[w];
+        }
+        const double incl = woff + iw;
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double b_i = p_b + carry;
+        const double carry_next = carry + total;
+        const double b_next = fmin(p_b + carry_next, p_next);
+        const double tb = b_i + excl;
+        const double cap = fmin(b_i + incl, b_next);
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++)
+            if (i0 + j < e1) a.su[i0 + j] = fmin(tb + r[j], cap);
+        carry = carry_next;
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int shard_of(const double *goff, const double *gpi, int world, double su) {
+    int k = 0;
+    while (k + 1 < world && su >= goff[k + 1]) k++;
+    while (k > 0 && !(gpi[k] > 0.0)) k--;
+    while (k + 1 < world && !(gpi[k] > 0.0)) k++;
+    return k;
+}
+
+// ---------------------------------------------------------------------------
+// the step kernel: resample_move + reweight_particles (+ compute_summaries of the previous step)
+// (core.py:323-367)
+// ---------------------------------------------------------------------------
+#ifndef SMCB_KU
+#define SMCB_KU 2
+#endif
+#ifndef SMCB_MINB
+#define SMCB_MINB 3
+#endif
+#ifdef SMCB_TRACE
+// per-CTA timeline of the LAST launch of the step kernel: {start, prologue done, main loop done, smid} in ns
+__device__ unsigned long long g_trace[4 * 2048];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+}
+#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[4 * blockIdx.x + (slot)] = gtimer(); } while (0)
+#else
+#define SMCB_TRACE_MARK(slot) do { } while (0)
+#endif
+
+template <class M, int FK, int SCHEME>
+__global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M model, FilterArgs a, long long t) {
+    constexpr bool APF = FkTraits<FK>::apf;
+    constexpr int D = M::D, NZ = M::NZ;
+    constexpr int kStage = 2048;                       // doubles of CDF staged per output tile
+    __shared__ StepSmem sh;
+    __shared__ double s_su[2];
+    __shared__ __align__(128) double s_cdf2[2][kStage];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ long long s_hi;
+    __shared__ double s_warp[kBlock / 32];
+#ifdef SMCB_TRACE
+    if (threadIdx.x == 0) { g_trace[4 * blockIdx.x] = gtimer(); g_trace[4 * blockIdx.x + 3] = smid(); }
+#endif
+    // everything below reads what the previous kernel of the stream wrote (programmatic dependent launch:
+    // this kernel may have been scheduled before its predecessor retired)
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    const StepDecision dec = step_prologue<APF>(a, t, sh, blockIdx.x == 0, true);
+    SMCB_TRACE_MARK(1);
+    const int cur = (int)((t - 1) & 1);                // step s writes buffers [s & 1]
+    const bool rs = dec.rs != 0;
+    const double reset_c = dec.reset_c;
+    const StepK k = step_consts(a, t);
+    const StepK kprev = step_consts(a, t - 1);
+    const double *__restrict__ Xi = a.X[cur];
+    const double *__restrict__ lwi = a.lw[cur];
+    double *__restrict__ Xo = a.X[cur ^ 1];
+    double *__restrict__ lwo = a.lw[cur ^ 1];
+    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const double *zin = a.z_in ? a.z_in + (size_t)t * NZ * n : nullptr;
+    const bool last_apf = APF && (t + 1 < a.T);
+    const bool mom = a.moments != nullptr || a.world > 1;
+    const bool vec_x = (D == 1) || ((n & 1) == 0);     // SoA component rows are 16-byte aligned
+
+    Acc<D> acc;
+    acc_init(acc);
+    Lse3 aux = lse3_empty();
+
+    // propagate + reweight one pair of particles; writes x', lw'; returns lw' (and the auxiliary
+    // log-weights of the next step for an APF), -inf in masked slots
+    auto do_pair = [&](int64_t p, const double (&xp)[2][D], const double (&base)[2], double (&x)[2][D], double *l,
+                       double *av) {
+        double z[2][NZ];
+#pragma unroll
+        for (int c = 0; c < NZ; c++) {
+            if (zin) {                                   // injected normals: (T, NZ, n)
+                const double *zz = zin + (size_t)c * n;
+                z[0][c] = zz[2 * p];
+                z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
+            } else {
+                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, (uint32_t)c,
+                                 z[0][c], z[1][c]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            double d;
+            model_move<M, FK>(model, k, xp[j], z[j], x[j], d);
+            l[j] = fix_nan(base[j] + d);                          // Weights.add, resampling.py:241-244
+            if (APF) av[j] = last_apf ? fix_nan(l[j] + model_logeta<M>(model, k, x[j])) : -CUDART_INF;
+        }
+        if (2 * p + 1 < n) {
+            if (vec_x) {
+#pragma unroll
+                for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; c++) { Xo[(size_t)c * n + 2 * p] = x[0][c]; Xo[(size_t)c * n + 2 * p + 1] = x[1][c]; }
+            }
+            st2(lwo + 2 * p, l[0], l[1]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) { Xo[(size_t)c * n + 2 * p] = x[0][c]; x[1][c] = 0.0; }
+            lwo[2 * p] = l[0];
+            l[1] = -CUDART_INF;
+            if (APF) av[1] = -CUDART_INF;
+        }
+    };
+
+    if (!rs) {
+        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread
+        constexpr int kU = SMCB_KU;
+        constexpr int64_t stride = kBlock;
+        const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
+        const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+        for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kU * stride) {
+            double xp[kU][2][D], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {                        // all loads first (MLP)
+                const int64_t p = p0 + u * stride;
+                if (p < pend && 2 * p + 1 < n) {
+                    double2 tl = ld2(lwi + 2 * p);
+                    base[u][0] = tl.x; base[u][1] = tl.y;
+#pragma unroll
+                    for (int c = 0; c < D; c++) {
+                        if (vec_x) {
+                            double2 tx = ld2(Xi + (size_t)c * n + 2 * p);
+                            xp[u][0][c] = tx.x; xp[u][1][c] = tx.y;
+                        } else {
+                            xp[u][0][c] = Xi[(size_t)c * n + 2 * p]; xp[u][1][c] = Xi[(size_t)c * n + 2 * p + 1];
+                        }
+                    }
+                } else if (p < pend) {
+                    base[u][0] = lwi[2 * p]; base[u][1] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; c++) { xp[u][0][c] = Xi[(size_t)c * n + 2 * p]; xp[u][1][c] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int64_t p = p0 + u * stride;
+                if (p < pend) {
+                    do_pair(p, xp[u], base[u], reinterpret_cast<double (&)[2][D]>(x[2 * u]), l + 2 * u,
+                            APF ? av + 2 * u : av);
+                } else {
+                    l[2 * u] = l[2 * u + 1] = -CUDART_INF;
+                    if (APF) av[APF ? 2 * u : 0] = av[APF ? 2 * u + 1 : 0] = -CUDART_INF;
+#pragma unroll
+                    for (int c = 0; c < D; c++) { x[2 * u][c] = 0.0; x[2 * u + 1][c] = 0.0; }
+                }
+            }
+            acc_add_batch<2 * kU, D>(acc, l, x, mom);
+            if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(aux, av);
+        }
+    } else {
+        // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
+        unsigned long long bar_target = (unsigned long long)gridDim.x *
+                                        ((unsigned long long)dec.nrs_prev * (SCHEME == SMCB_RS_MULTINOMIAL ? 2 : 1));
+        scan_own_range<M, FK>(model, a, t, cur, dec, s_warp);
+        if (SCHEME == SMCB_RS_MULTINOMIAL) {
+            spacings_pass1(a, t, sh);
+            bar_target += gridDim.x;
+            grid_barrier(a, bar_target);
+            spacings_pass2(a, sh, s_warp);
+        }
+        bar_target += gridDim.x;
+        grid_barrier(a, bar_target);
+        const int64_t ntiles = (npairs + kBlock - 1) / kBlock;
+        const int64_t per = a.chunk / kBlock;                  // chunk is a multiple of kBlock
+        const int64_t tile_lo = (int64_t)blockIdx.x * per;
+        const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
+        const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
+        double u_sys = 0.0;
+        if (SCHEME == SMCB_RS_SYSTEMATIC) {
+            if (uin) u_sys = uin[0];
+            else { double u1; uniform_pair(a.key, 0ull, (uint32_t)t, kPurposeUniform, u_sys, u1); }
+        }
+        // shared tail of both searches: gather the ancestors' states, restart weights, propagate
+        auto finish_pair = [&](int64_t p, const double *X0, const double *X1, int64_t a0, int64_t a1, long long g0,
+                               long long g1) {
+            double xp[2][D], base[2], x[2][D];
+#pragma unroll
+            for (int c = 0; c < D; c++) {                // Xp = X[A], component-wise (SoA)
+                xp[0][c] = __ldg(X0 + (size_t)c * n + a0);
+                xp[1][c] = __ldg(X1 + (size_t)c * n + a1);
+            }
+            if (APF) {   // core.py:302: lw = log_mean_exp(logetat, W) - logetat[A]
+                base[0] = reset_c - model_logeta<M>(model, kprev, xp[0]);
+                base[1] = reset_c - model_logeta<M>(model, kprev, xp[1]);
+            } else {     // Weights() then add(delta): lw = 0 + delta (shard mass if sharded)
+                base[0] = reset_c; base[1] = reset_c;
+            }
+            if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(g0, g1);
+            else a.A[2 * p] = g0;
+            double l[2], av[2];
+            do_pair(p, xp, base, x, l, av);
+            acc_add_batch<2, D>(acc, l, x, mom);
+            if (APF) lse3_add_batch<2>(aux, av);
+        };
+        if (!a.rs_global) {
+            const double M_ = (double)n;
+            const double zlast = (SCHEME == SMCB_RS_MULTINOMIAL) ? __ldcg(a.su + n) : 1.0;
+            int64_t lo = -1;
+            if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init_fence(); }
+            __syncthreads();
+            uint32_t phase0 = 0, phase1 = 0;
+            int buf = 0;
+            // thread 0: bring cdf[sb, sb + c) into buffer b (sb = lo_ rounded down to even => 16-byte aligned)
+            // by ONE TMA bulk copy (cp.async.bulk + mbarrier); the slice of tile i+1 is in flight while tile i
+            // propagates and reweights
+            auto issue = [&](int64_t lo_, int b) {
+                const int64_t sb = lo_ & ~(int64_t)1;
+                const int c = (int)((n - sb) < kStage ? (n - sb) : kStage);
+                const uint32_t bytes = (uint32_t)(c & ~1) * 8u;
+                if (c & 1) s_cdf2[b][c - 1] = __ldcg(a.cdf + sb + c - 1);      // odd tail (n odd, end of the array)
+                if (bytes) {
+                    mbar_arrive_expect_tx(&s_bar[b], bytes);
+                    tma_bulk_g2s(&s_cdf2[b][0], a.cdf + sb, bytes, &s_bar[b]);
+                } else {
+                    mbar_arrive(&s_bar[b]);
+                }
+            };
+            for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
+                const int64_t p = tile * kBlock + threadIdx.x;
+                const int64_t k0 = 2 * tile * kBlock;
+                const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+                double su[2] = {2.0, 2.0};
+                if (p < npairs) {
+                    if (SCHEME == SMCB_RS_SYSTEMATIC) {                    // resampling.py:609
+                        su[0] = (u_sys + (double)(2 * p)) / M_;
+                        su[1] = (u_sys + (double)(2 * p + 1)) / M_;
+                    } else if (SCHEME == SMCB_RS_STRATIFIED) {             // resampling.py:602
+                        double u0, u1;
+                        if (uin) { u0 = uin[2 * p]; u1 = (2 * p + 1 < n) ? uin[2 * p + 1] : 0.0; }
+                        else uniform_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t,
+                                          kPurposeUniform, u0, u1);
+                        su[0] = (u0 + (double)(2 * p)) / M_;
+                        su[1] = (u1 + (double)(2 * p + 1)) / M_;
+                    } else {                                               // resampling.py:537
+                        su[0] = __ldcg(a.su + 2 * p) / zlast;
+                        su[1] = (2 * p + 1 < n) ? __ldcg(a.su + 2 * p + 1) / zlast : 2.0;
+                    }
+                    if (2 * p == k0) s_su[0] = su[0];
+                    if (2 * p == k1) s_su[1] = su[0];
+                    if (2 * p + 1 == k1) s_su[1] = su[1];
+                }
+                __syncthreads();
+                const double su_first = s_su[0], su_last = s_su[1];
+                if (lo < 0) {                                      // first tile of this block
+                    lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
+                    lo = lo < n - 1 ? lo : n - 1;
+                    if (threadIdx.x == 0) issue(lo, buf);
+                    __syncthreads();
+                }
+                // su is sorted, so the slice starts at `lo`
+                const int64_t sbase = lo & ~(int64_t)1;
+                const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
+                mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
+                if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+                const double *s_cdf = s_cdf2[buf];
+                const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= su_last);
+                int64_t hi = lo;
+                if (!covered) hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);   // rare: sparse mass
+                int64_t a0 = 0, a1 = 0;
+                if (p < npairs) {
+                    if (covered) {
+                        int l0 = (int)(lo - sbase), h0 = cnt;
+                        while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < su[0]) l0 = mid + 1; else h0 = mid; }
+                        // su[1] >= su[0] and on average one CDF entry per output: walk forward a few
+                        // entries before falling back to bisection (same result as searchsorted)
+                        int l1 = l0, h1 = cnt;
+#pragma unroll
+                        for (int w = 0; w < 4; w++)
+                            if (l1 < cnt && s_cdf[l1] < su[1]) l1++;
+                        if (l1 < cnt && s_cdf[l1] < su[1]) {
+                            while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < su[1]) l1 = mid + 1; else h1 = mid; }
+                        }
+                        a0 = sbase + l0;
+                        a1 = sbase + l1;
+                        if (2 * p == k1) s_hi = a0;
+                        if (2 * p + 1 == k1) s_hi = a1;
+                    } else {
+                        const int64_t hi1 = hi < n ? hi + 1 : n;
+                        a0 = lower_bound(a.cdf, lo, hi1, su[0]);
+                        a1 = lower_bound(a.cdf, a0, hi1, su[1]);
+                    }
+                }
+                __syncthreads();                                   // s_hi published; buffer buf^1 is free
+                const int64_t lo_next = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
+                if (tile + 1 < tile_hi && threadIdx.x == 0) issue(lo_next, buf ^ 1);
+                if (p < npairs) {
+                    a0 = a0 < n - 1 ? a0 : n - 1;
+                    a1 = a1 < n - 1 ? a1 : n - 1;
+                    finish_pair(p, Xi, Xi, a0, a1, a0, a1);
+                }
+                lo = lo_next;
+                buf ^= 1;
+            }
+        } else {
+            // exact global resampling over particle shards (mode 2; resampling.py:599-610
+            // applied to the concatenation of all shards).  Output j of rank r is global offspring index_offset + j:
+            // its grid point su is located in the global CDF in two levels -- shard k with goff[k] <= su < goff[k+1]
+            // (offsets from the exchanged statistics, identical bits on every rank), then v = (su - goff[k]) / gpi[k]
+            // in shard k's own normalised CDF, read over NVLink -- and the ancestor's state is pulled from shard k's
+            // particle buffer.  First: tell every peer that this shard's CDF of step t is complete, and wait for theirs.
+            if (blockIdx.x == 0 && (int)threadIdx.x < a.world) {
+                __threadfence_system();
+                double *slot = a.mail_peer[threadIdx.x] + ((size_t)(t & 1) * a.world + a.rank) * kMailStride;
+                *reinterpret_cast<volatile double *>(slot + kMailScan) = (double)(t + 1);
+            }
+            if ((int)threadIdx.x < a.world)
+                wait_epoch(a.mail_local + ((size_t)(t & 1) * a.world + threadIdx.x) * kMailStride + kMailScan,
+                           (double)(t + 1), a.sync_timeout);
+            __syncthreads();
+            const int world = a.world;
+            const double M_ = (double)a.n_global;
+            double *s_cdf = s_cdf2[0];
+            int64_t lo = -1;
+            int lo_shard = -1;
+            const int64_t npairs_e = n >> 1;                        // sharded filters have even n
+            for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
+                const int64_t p = tile * kBlock + threadIdx.x;
+                const int64_t k0 = 2 * tile * kBlock;
+                const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+                double su[2] = {2.0, 2.0};
+                if (p < npairs_e) {
+                    const double g0 = (double)(a.index_offset + 2 * p);
+                    if (SCHEME == SMCB_RS_SYSTEMATIC) {
+                        su[0] = (u_sys + g0) / M_;
+                        su[1] = (u_sys + (g0 + 1.0)) / M_;
+                    } else {
+                        double u0, u1;
+                        if (uin) { u0 = uin[2 * p]; u1 = uin[2 * p + 1]; }
+                        else uniform_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, kPurposeUniform, u0, u1);
+                        su[0] = (u0 + g0) / M_;
+                        su[1] = (u1 + (g0 + 1.0)) / M_;
+                    }
+                    if (2 * p == k0) s_su[0] = su[0];
+                    if (2 * p + 1 == k1) s_su[1] = su[1];
+                }
+                __syncthreads();
+                const double su_first = s_su[0], su_last = s_su[1];
+                const int kf = shard_of(sh.goff, sh.gpi, world, su_first);
+                const int kl = shard_of(sh.goff, sh.gpi, world, su_last);
+                int ks[2] = {kf, kf};
+                int64_t an[2] = {0, 0};
+                if (kf == kl) {
+                    // the whole tile draws from one shard: staged search on that shard's CDF with the grid
+                    // points mapped into its local scale
+                    const double *cdf = a.pcdf[kf];
+                    const double off = sh.goff[kf], pi = sh.gpi[kf];
+                    const double v0 = fmin((su[0] - off) / pi, 1.0), v1 = fmin((su[1] - off) / pi, 1.0);
+                    const double v_first = fmin((su_first - off) / pi, 1.0), v_last = fmin((su_last - off) / pi, 1.0);
+                    if (lo < 0 || lo_shard != kf) lo = block_lower_bound<kBlock>(cdf, 0, n, v_first);
+                    if (lo > n - 1) lo = n - 1;
+                    lo_shard = kf;
+                    const int64_t sbase = lo & ~(int64_t)1;
+                    const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
+                    for (int i = 2 * threadIdx.x; i < cnt; i += 2 * kBlock) {
+                        if (i + 1 < cnt) *reinterpret_cast<double2 *>(&s_cdf[i]) = __ldcg(reinterpret_cast<const double2 *>(cdf + sbase + i));
+                        else s_cdf[i] = __ldcg(cdf + sbase + i);
+                    }
+                    __syncthreads();
+                    const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= v_last);
+                    int64_t hi = lo;
+                    if (!covered) hi = block_lower_bound<kBlock>(cdf, lo, n, v_last);
+                    if (p < npairs_e) {
+                        if (covered) {
+                            int l0 = (int)(lo - sbase), h0 = cnt;
+                            while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < v0) l0 = mid + 1; else h0 = mid; }
+                            int l1 = l0, h1 = cnt;
+#pragma unroll
+                            for (int w = 0; w < 4; w++)
+                                if (l1 < cnt && s_cdf[l1] < v1) l1++;
+                            if (l1 < cnt && s_cdf[l1] < v1) {
+                                while (l1 < h1) { const int mid = (l1 + h1) >> 1; if (s_cdf[mid] < v1) l1 = mid + 1; else h1 = mid; }
+                            }
+                            an[0] = sbase + l0;
+                            an[1] = sbase + l1;
+                            if (2 * p + 1 == k1) s_hi = an[1];
+                        } else {
+                            const int64_t hi1 = hi < n ? hi + 1 : n;
+                            an[0] = lower_bound(cdf, lo, hi1, v0);
+                            an[1] = lower_bound(cdf, an[0], hi1, v1);
+                        }
+                    }
+                    __syncthreads();
+                    lo = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
+                } else {
+                    // the tile straddles a shard boundary (at most world - 1 tiles per rank): plain searches
+                    if (p < npairs_e) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            ks[j] = shard_of(sh.goff, sh.gpi, world, su[j]);
+                            const double v = fmin((su[j] - sh.goff[ks[j]]) / sh.gpi[ks[j]], 1.0);
+                            an[j] = lower_bound(a.pcdf[ks[j]], 0, n, v);
+                        }
+                    }
+                    lo = -1;
+                }
+                if (p < npairs_e) {
+                    const int64_t a0 = an[0] < n - 1 ? an[0] : n - 1, a1 = an[1] < n - 1 ? an[1] : n - 1;
+                    // ancestors are GLOBAL particle indices
+                    finish_pair(p, a.pX[ks[0]][cur], a.pX[ks[1]][cur], a0, a1, (long long)ks[0] * n + a0,
+                                (long long)ks[1] * n + a1);
+                }
+                __syncthreads();       // s_su / s_hi / s_cdf are rewritten by the next tile
+            }
+        }
+    }
+    SMCB_TRACE_MARK(2);
+    write_partial<D, APF>(a, t, acc, aux, mom, sh);
+}
+
+// the prologue alone (one CTA): finalises the last enqueued step so that the host can read its summaries
+template <bool APF>
+__global__ void __launch_bounds__(kBlock) k_tail(FilterArgs a, long long t) {
+    __shared__ StepSmem sh;
+    cudaGridDependencySynchronize();
+    step_prologue<APF>(a, t, sh, true, false);
+}
+
+// sharded filters with the host-driven exchange: this shard's statistics of step s -> local_stats
+template <bool APF>
+__global__ void __launch_bounds__(kBlock) k_publish(FilterArgs a, long long s) {
+    __shared__ StepSmem sh;
+    FilterArgs b = a;
+    b.world = 1;                       // local merge only
+    b.moments = nullptr;
+    b.summaries = nullptr;
+    // reuse the prologue's fixed-order merge by running it on the local rows; it returns the shard totals
+    // through the partial row 0 of the OTHER parity?  No: keep it explicit and simple here.
+    const int G = a.grid, tid = threadIdx.x;
+    const double *part = a.partials + (size_t)(s & 1) * kMaxGrid * kPartStride;
+    const int b0 = tid * kPer;
+    double mx[2] = {-CUDART_INF, -CUDART_INF};
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const int r = b0 + i;
+        if (r < G) {
+            const double m0 = __ldcg(part + (size_t)r * kPartStride), m1 = __ldcg(part + (size_t)r * kPartStride + 4);
+            mx[0] = (m0 > mx[0] || m0 != m0) ? m0 : mx[0];
+            mx[1] = (m1 > mx[1] || m1 != m1) ? m1 : mx[1];
+        }
+    }
+    block_max_all<2>(mx, sh.red);
+    double v[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) v[j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        const int r = b0 + i;
+        if (r < G) {
+            const double *row = part + (size_t)r * kPartStride;
+            const double ew = shift_factor(__ldcg(row), mx[0]), ea = shift_factor(__ldcg(row + 4), mx[1]);
+            v[0] += __ldcg(row + 1) * ew;
+            v[1] += __ldcg(row + 2) * (ew * ew);
+            v[2] += __ldcg(row + 5) * ea;
+            v[3] += __ldcg(row + 6) * (ea * ea);
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[4 + c] += __ldcg(row + 8 + c) * ew;
+        }
+    }
+    block_sum_all<12>(v, sh.red);
+    if (tid == 0) {
+        double *o = a.local_stats;
+        o[0] = mx[0]; o[1] = v[0]; o[2] = v[1]; o[3] = 0.0;
+        o[4] = mx[1]; o[5] = v[2]; o[6] = v[3]; o[7] = 0.0;
+        for (int c = 0; c < 8; c++) o[8 + c] = v[4 + c];
+    }
+}
+
+}  // namespace smcb
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct smcb_filter {
+    smcb_ctx *ctx;
+    smcb_filter_desc desc;
+    FilterArgs args;
+    char *mem;            // header (StepState[2], barrier, timeout flag) + partials + block aggregates
+    int grid_move;
+    int blocks_per_sm;    // resident CTAs/SM of the step kernel (persistent grid = SMs x this)
+    int64_t t_host;       // steps launched so far (the device needs no other notion of time)
+    int64_t t_tail;       // the step count the last k_tail was launched for (-1: none)
+    bool pdl, coop;       // launch attributes in use (programmatic dependent launch, cooperative)
+    int (*launch_init)(smcb_filter *);
+    int (*launch_step)(smcb_filter *);
+    int (*launch_tail)(smcb_filter *);
+    int (*launch_publish)(smcb_filter *);
+};
+
+template <class... Args>
+static int launch_ex(smcb_filter *f, void (*kern)(Args...), int grid, bool coop, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = f->ctx->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (coop) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; na++; }
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    SMCB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+    f->ctx->launches++;
+    return SMCB_OK;
+}
+
+template <class M, int FK, int SCHEME>
+static int launch_step_t(smcb_filter *f) {
+    M model;
+    model.load(f->desc.params);
+    return launch_ex(f, k_step<M, FK, SCHEME>, f->grid_move, f->coop, f->pdl, model, f->args, (long long)f->t_host);
+}
+
+template <class M, int FK>
+static int launch_init_t(smcb_filter *f) {
+    M model;
+    model.load(f->desc.params);
+    k_init<M, FK><<<f->grid_move, kBlock, 0, f->ctx->stream>>>(model, f->args);
+    f->ctx->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
+template <int FK>
+static int launch_tail_t(smcb_filter *f) {
+    return launch_ex(f, k_tail<FkTraits<FK>::apf>, 1, false, f->pdl, f->args, (long long)f->t_host);
+}
+
+template <int FK>
+static int launch_publish_t(smcb_filter *f) {
+    k_publish<FkTraits<FK>::apf><<<1, kBlock, 0, f->ctx->stream>>>(f->args, (long long)(f->t_host - 1));
+    f->ctx->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
+template <class M, int FK, int SCHEME>
+static int bind_one(smcb_filter *f) {
+    f->launch_init = launch_init_t<M, FK>;
+    f->launch_step = launch_step_t<M, FK, SCHEME>;
+    f->launch_tail = launch_tail_t<FK>;
+    f->launch_publish = launch_publish_t<FK>;
+    int nb = 0;
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step<M, FK, SCHEME>, kBlock, 0));
+    f->blocks_per_sm = nb < 1 ? 1 : nb;
+    return SMCB_OK;
+}
+
+template <class M, int FK>
+static int bind_scheme(smcb_filter *f) {
+    switch (f->desc.scheme) {
+        case SMCB_RS_SYSTEMATIC: return bind_one<M, FK, SMCB_RS_SYSTEMATIC>(f);
+        case SMCB_RS_STRATIFIED: return bind_one<M, FK, SMCB_RS_STRATIFIED>(f);
+        case SMCB_RS_MULTINOMIAL: return bind_one<M, FK, SMCB_RS_MULTINOMIAL>(f);
+        default:
+            set_error("fused filter: resampling scheme %d is not fused (use systematic, stratified or "
+                      "multinomial, or the unfused path)", f->desc.scheme);
+            return SMCB_ENOSYS;
+    }
+}
+
+template <class M>
+static int bind_fk(smcb_filter *f) {
+    switch (f->desc.fk) {
+        case SMCB_FK_BOOTSTRAP: return bind_scheme<M, SMCB_FK_BOOTSTRAP>(f);
+        case SMCB_FK_GUIDED:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_GUIDED>(f);
+        case SMCB_FK_APF:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_APF>(f);
+        case SMCB_FK_AUXBOOT:
+            if (!M::has_proposal) break;
+            return bind_scheme<M, SMCB_FK_AUXBOOT>(f);
+        default:
+            set_error("fused filter: unknown Feynman-Kac kind %d", f->desc.fk);
+            return SMCB_EINVAL;
+    }
+    // the reference raises NotImplementedError from StateSpaceModel.proposal / logeta
+    set_error("fused filter: model %d implements no proposal/logeta (Feynman-Kac kind %d)",
+              f->desc.model, f->desc.fk);
+    return SMCB_ENOSYS;
+}

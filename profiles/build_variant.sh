@@ -11,6 +11,6 @@ mkdir -p particles_b200/variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC \
      -DSMCB_BENCH_ONLY "$@" -c $C/smcb_filter.cu -o /tmp/smcb_filter_$name.o
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o particles_b200/variants/libsmcb_$name.so \
-     /tmp/smcb_filter_$name.o $C/smcb_api.o $C/smcb_filter_1d.o $C/smcb_filter_nd.o $C/smcb_sampler.o \
+     /tmp/smcb_filter_$name.o $C/smcb_api.o $C/smcb_filter_1d.o $C/smcb_filter_nd.o $C/smcb_sampler.o $C/smcb_peaks.o \
      -lcudart_static -lpthread -ldl -lrt
 echo particles_b200/variants/libsmcb_$name.so
