@@ -157,8 +157,9 @@ int smcb_logistic_wf_move(smcb_ctx *ctx, int64_t M, int d, int P, const double *
                           double *theta_out, double *lprior_out, double *llik_out, double *lpost_out,
                           double *pb_out);
 
-/* test hook: the step kernel's own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
- * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1) */
+/* test hook: the kernels' own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
+ * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1)   -- polynomial family;
+ *     4 exp, 5 log, 6 sin(2 pi x), 7 cos(2 pi x), 8 sqrt (x > 0, normal)        -- table family (step kernels) */
 int smcb_device_math(smcb_ctx *ctx, int fn, const double *x, double *out, int64_t n);
 
 /* ---------------------------------------------------------------------------
@@ -205,20 +206,22 @@ typedef struct {
     const double *u_in; /* NULL, or injected uniforms: (T, n + 1)                   */
     double *scratch;    /* NULL, or n + 2 doubles (multinomial: exponential spacings) */
     const double *step_consts; /* NULL, or (T) host-computed per-step model constants */
-    double *local_stats;       /* world > 1: 8 doubles, this rank's weight statistics     */
-    const double *gathered;    /* world > 1: world x 8 doubles, filled by the all-gather  */
+    double *local_stats;       /* world > 1: 16 doubles, this rank's weight statistics    */
+    const double *gathered;    /* world > 1: world x 16 doubles, filled by the all-gather */
     double *mail_local;        /* world > 1, optional: this rank's peer mailbox (smcb_p2p_alloc,
-                                  2 * world * 16 doubles) -> statistics are exchanged by the
+                                  2 * world * 32 doubles) -> statistics are exchanged by the
                                   kernels themselves over NVLink and smcb_filter_step works */
     double *mail_peer[8];      /* every rank's mailbox as mapped in THIS process (own = mail_local) */
     /* world > 1, optional: EXACT global resampling (mode 2).  X[0], X[1] and cdf
        of every rank live in peer-mapped memory (smcb_p2p_alloc); on a resampling step each rank
        searches the global CDF (shard offsets from the exchanged statistics + the owning shard's
-       local CDF) and pulls the selected ancestors over NVLink.  Needs mail_local; Feynman-Kac
-       kinds without auxiliary weights (bootstrap, guided); systematic or stratified. */
+       local CDF) and pulls the selected ancestors over NVLink.  Needs mail_local; systematic or
+       stratified. */
     int32_t rs_global, reserved0;
-    double *stage_X;           /* (d, n) gathered ancestors of a global resampling step   */
-    double *stage_lw;          /* (n)    their restart log-weights                        */
+    double *moments;           /* NULL, or (T, 8): per step the weighted mean [0..3] and variance [4..7] of the
+                                  state components (collectors.Moments with the default wmean_and_var,
+                                  collectors.py:301-317, resampling.py:320-338), accumulated by the step kernel */
+    double *reserved1;
     const double *peer_X0[8];  /* rank r's X[0] / X[1] / cdf as mapped in THIS process    */
     const double *peer_X1[8];
     const double *peer_cdf[8];
@@ -226,14 +229,15 @@ typedef struct {
 
 int smcb_filter_create(smcb_ctx *ctx, const smcb_filter_desc *desc, smcb_filter **out);
 int smcb_filter_destroy(smcb_filter *f);
-/* enqueue nsteps steps of SMC.__next__ (core.py:369-383); no host sync */
+/* enqueue nsteps steps of SMC.__next__ (core.py:369-383); no host sync.  ONE kernel launch per step (its
+ * prologue finalises the previous step) plus one single-CTA launch that finalises the last step of the batch. */
 int smcb_filter_step(smcb_filter *f, int64_t nsteps);
 /* sharded filter: particles are partitioned over `world` GPUs, one
- * process each.  A step is step_local (this rank's kernels, ending with its (max, sum exp,
- * sum exp^2) in desc.local_stats), ONE all-gather of 8 doubles per rank into desc.gathered
- * done by the host layer on the same stream (NCCL), and step_finish (global log-normaliser,
- * ESS, logLt recursion and the resampling decision, identical on every rank).  Resampling is
- * per shard with the shard's mass carried in the restart log-weight. */
+ * process each.  With the host-driven exchange a step is step_local (this rank's kernels, ending
+ * with its (max, sum exp, sum exp^2 [, moments]) in desc.local_stats), ONE all-gather of 16 doubles
+ * per rank into desc.gathered done by the host layer on the same stream (NCCL), and step_finish
+ * (global log-normaliser, ESS, logLt recursion and the resampling decision, identical on every
+ * rank).  Resampling is per shard with the shard's mass carried in the restart log-weight. */
 int smcb_filter_step_local(smcb_filter *f);
 int smcb_filter_step_finish(smcb_filter *f);
 /* peer memory for the fused exchange: alloc (zeroed) + 64-byte IPC handle to hand to the other
@@ -243,8 +247,8 @@ int smcb_p2p_open(smcb_ctx *ctx, const unsigned char *handle64, void **dev_ptr);
 int smcb_p2p_close(void *peer_ptr);
 int smcb_p2p_free(void *dev_ptr);
 /* same, with a CUDA-event pair around every kernel launch; synchronises at the end.
- * out[0..3] = summed device ms of {init, weight-scan, spacings-scan, move} kernels,
- * out[4..7] = launches of each (bench.py "roofline") */
+ * out[0..3] = summed device ms of {init, step kernels of resampling steps, tail, step kernels of
+ * non-resampling steps}, out[4..7] = launches of each (bench.py "roofline") */
 int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *out8);
 /* host-visible snapshot (synchronises the stream):
  * out[0]=t, [1]=cur buffer index, [2]=rs_flag of last step, [3]=logLt, [4]=ESS,

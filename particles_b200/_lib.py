@@ -33,7 +33,7 @@ class FilterDesc(C.Structure):
         ("summaries", c_dp), ("z_in", c_dp), ("u_in", c_dp), ("scratch", c_dp),
         ("step_consts", c_dp), ("local_stats", c_dp), ("gathered", c_dp),
         ("mail_local", c_dp), ("mail_peer", c_dp * 8),
-        ("rs_global", C.c_int32), ("reserved0", C.c_int32), ("stage_X", c_dp), ("stage_lw", c_dp),
+        ("rs_global", C.c_int32), ("reserved0", C.c_int32), ("moments", c_dp), ("reserved1", c_dp),
         ("peer_X0", c_dp * 8), ("peer_X1", c_dp * 8), ("peer_cdf", c_dp * 8),
     ]
 

@@ -80,15 +80,40 @@ class Summaries:
     def only_defaults(self):
         return len(self._collectors) == self._n_default
 
+    def device_moments(self, fk):
+        """True when every non-default collector is ``Moments()`` with the default ``mom_func`` and the model keeps
+        ``FeynmanKac.default_moments`` (resampling.wmean_and_var): exactly what the fused step kernel accumulates."""
+        extra = self._collectors[self._n_default:]
+        if not extra or not all(type(c) is Moments and c.mom_func is None for c in extra):
+            return False
+        dm = getattr(type(fk), "default_moments", None)
+        return getattr(dm, "__qualname__", "") == "FeynmanKac.default_moments"
+
     def collect(self, smc):
         for col in self._collectors:
-            col.collect(smc)
+            if type(col) is Moments and col.mom_func is None and getattr(smc, "_dev_moments", False):
+                col.summary.append(_moments_row(smc._engine.mom[smc._done - 1].cpu().numpy(), smc._engine.dim))
+            else:
+                col.collect(smc)
+
+    def _extend_moments(self, table, dim):
+        """Bulk fill of every ``Moments`` collector from the (T, 8) device table (fused ``run()``)."""
+        rows = [_moments_row(r, dim) for r in table]
+        for col in self._collectors[self._n_default:]:
+            col.summary.extend(dict(r) for r in rows)
 
     def _extend_defaults(self, ess, loglt, rs):
         """Bulk fill from the device table (fused ``run()``)."""
         self.ESSs.extend(ess)
         self.logLts.extend(loglt)
         self.rs_flags.extend(rs)
+
+
+def _moments_row(r, dim):
+    """One row of the device table -> what resampling.wmean_and_var returns (resampling.py:320-338)."""
+    if dim == 1:
+        return {"mean": float(r[0]), "var": float(r[4])}
+    return {"mean": r[:dim].copy(), "var": r[4:4 + dim].copy()}
 
 
 def default_moments(W, X):

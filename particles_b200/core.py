@@ -70,14 +70,13 @@ class _FusedEngine:
     """Owns the device buffers of one fused filter and the smcb_filter handle."""
 
     def __init__(self, spec, N, scheme, ESSrmin, seed, noise=None, n_global=None, index_offset=0,
-                 world=1, rank=0, group=None, p2p=False, global_rs=False):
+                 world=1, rank=0, group=None, p2p=False, global_rs=False, moments=False):
         self.world, self.rank, self.group = int(world), int(rank), group
         self.p2p = bool(p2p) and self.world > 1
         self.global_rs = bool(global_rs) and self.world > 1
         if self.global_rs and not self.p2p:
             raise ValueError("global resampling over shards needs the peer-memory exchange (exchange='p2p')")
-        self._mail_local, self._mail_peers = None, []
-        self._arena_local, self._arena_peers = None, []
+        self._pool = None
         self.ctx = context()
         self.lib = self.ctx.lib
         self.N, self.T = int(N), int(spec["data"].shape[0])
@@ -86,18 +85,21 @@ class _FusedEngine:
         dev = self.ctx.device
         f64 = dict(dtype=torch.float64, device=dev)
         xshape = (n,) if self.dim == 1 else (self.dim, n)      # SoA: component-major
+        if self.p2p:
+            self._pool = _p2p_pool(self.ctx, self.world, self.rank, group)
         if self.global_rs:      # particles and CDF in peer-mapped memory: peers pull ancestors from it
-            arena = self._open_arena((2 * self.dim + 1) * n * 8)
+            arena = self._pool.arena((2 * self.dim + 1) * n * 8)
             nd = self.dim * n
-            self.X = [tensor_from_ptr(arena, xshape), tensor_from_ptr(arena + nd * 8, xshape)]
-            self.cdf = tensor_from_ptr(arena + 2 * nd * 8, (n,))
-            self.stage_X, self.stage_lw = torch.empty(xshape, **f64), torch.empty(n, **f64)
+            self.X = [tensor_from_ptr(arena, xshape, owner=self._pool), tensor_from_ptr(arena + nd * 8, xshape, owner=self._pool)]
+            self.cdf = tensor_from_ptr(arena + 2 * nd * 8, (n,), owner=self._pool)
         else:
             self.X = [torch.empty(xshape, **f64), torch.empty(xshape, **f64)]
             self.cdf = torch.empty(n, **f64)
         self.lw = [torch.empty(n, **f64), torch.empty(n, **f64)]
         self.A = torch.empty(n, dtype=torch.int64, device=dev)
         self.summ = torch.zeros((T, _lib.SUMMARY_STRIDE), **f64)
+        # collectors.Moments on the device: per step the weighted mean / variance of every component
+        self.mom = torch.zeros((T, 8), **f64) if moments else None
         # the observations are the only per-run host input of this path: pinned -> device
         self.data_host = torch.from_numpy(spec["data"].reshape(-1)).pin_memory()
         self.data = self.data_host.to(dev, non_blocking=True)
@@ -126,65 +128,27 @@ class _FusedEngine:
         d.u_in = self.u_in.data_ptr() if self.u_in is not None else None
         d.scratch = self.scratch.data_ptr() if self.scratch is not None else None
         d.step_consts = self.sc.data_ptr() if self.sc is not None else None
+        d.moments = self.mom.data_ptr() if self.mom is not None else None
         d.world, d.rank = self.world, self.rank
-        if self.world > 1:      # per-step exchange buffers of the sharded filter (8 doubles / rank)
-            self.local_stats = torch.zeros(8, **f64)
-            self.gathered = torch.zeros(8 * self.world, **f64)
+        if self.world > 1:      # per-step exchange buffers of the sharded filter (16 doubles / rank)
+            self.local_stats = torch.zeros(16, **f64)
+            self.gathered = torch.zeros(16 * self.world, **f64)
             d.local_stats, d.gathered = self.local_stats.data_ptr(), self.gathered.data_ptr()
             if self.p2p:
-                self._open_mailboxes(d)
+                mail = self._pool.mailbox()
+                d.mail_local = mail[self.rank]
+                for r in range(self.world):
+                    d.mail_peer[r] = mail[r]
             if self.global_rs:
                 nd = self.dim * n * 8
                 d.rs_global = 1
-                d.stage_X, d.stage_lw = self.stage_X.data_ptr(), self.stage_lw.data_ptr()
                 for r in range(self.world):
-                    base = self._arena_local if r == self.rank else self._arena_by_rank[r]
+                    base = self._pool.arena_of(r)
                     d.peer_X0[r], d.peer_X1[r], d.peer_cdf[r] = base, base + nd, base + 2 * nd
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(self.ctx.handle, C.byref(d), C.byref(h)))
         self.handle = h
-
-    def _open_mailboxes(self, d):
-        """Peer-memory exchange: every rank allocates a small mailbox, the 64-byte CUDA IPC
-        handles travel through torch.distributed once, each rank maps its peers' mailboxes."""
-        import torch.distributed as dist
-        ptr_ = C.c_void_p()
-        hbuf = C.create_string_buffer(64)
-        _lib.check(self.lib.smcb_p2p_alloc(self.ctx.handle, 2 * self.world * 16 * 8, C.byref(ptr_), hbuf))
-        self._mail_local = ptr_.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
-        d.mail_local = self._mail_local
-        for r in range(self.world):
-            if r == self.rank:
-                d.mail_peer[r] = self._mail_local
-                continue
-            pp = C.c_void_p()
-            _lib.check(self.lib.smcb_p2p_open(self.ctx.handle, handles[r], C.byref(pp)))
-            self._mail_peers.append(pp.value)
-            d.mail_peer[r] = pp.value
-        dist.barrier(group=self.group)       # every mailbox is mapped before anybody writes
-
-    def _open_arena(self, nbytes):
-        """Global resampling: this rank's X[0] | X[1] | cdf in one IPC-shareable allocation, mapped by
-        every peer (same exchange of handles as the mailboxes)."""
-        import torch.distributed as dist
-        ptr_ = C.c_void_p()
-        hbuf = C.create_string_buffer(64)
-        _lib.check(self.lib.smcb_p2p_alloc(self.ctx.handle, int(nbytes), C.byref(ptr_), hbuf))
-        self._arena_local = ptr_.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
-        self._arena_by_rank = {}
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            pp = C.c_void_p()
-            _lib.check(self.lib.smcb_p2p_open(self.ctx.handle, handles[r], C.byref(pp)))
-            self._arena_peers.append(pp.value)
-            self._arena_by_rank[r] = pp.value
-        return self._arena_local
 
     def step(self, nsteps=1):
         self.ctx.bind_stream()
@@ -202,8 +166,8 @@ class _FusedEngine:
         self.ctx.bind_stream()
         out = (C.c_double * 8)()
         _lib.check(self.lib.smcb_filter_step_timed(self.handle, int(nsteps), out))
-        ms = dict(zip(("init", "scan", "spacings", "move"), out[0:4]))
-        cnt = dict(zip(("init", "scan", "spacings", "move"), (int(v) for v in out[4:8])))
+        ms = dict(zip(("init", "step_rs", "tail", "step"), out[0:4]))
+        cnt = dict(zip(("init", "step_rs", "tail", "step"), (int(v) for v in out[4:8])))
         return ms, cnt
 
     def state(self):
@@ -212,29 +176,88 @@ class _FusedEngine:
         return list(out)
 
     def close(self):
+        """Free the filter handle.  Peer-mapped memory (mailboxes, arenas) belongs to the per-(process, group)
+        pool and stays mapped for the next sharded filter, so closing needs no collective call."""
         if getattr(self, "handle", None):
-            self.lib.smcb_filter_destroy(self.handle)
+            self.lib.smcb_filter_destroy(self.handle)      # synchronises this rank's stream
             self.handle = None
-            if self._mail_local:
-                import torch.distributed as dist
-                torch.cuda.synchronize()
-                dist.barrier(group=self.group)       # nobody still writes into a mailbox
-                for pp in self._mail_peers:
-                    self.lib.smcb_p2p_close(C.c_void_p(pp))
-                self.lib.smcb_p2p_free(C.c_void_p(self._mail_local))
-                self._mail_local, self._mail_peers = None, []
-            if self._arena_local:                    # after the barrier above: no peer still reads it
-                for pp in self._arena_peers:
-                    self.lib.smcb_p2p_close(C.c_void_p(pp))
-                self.X = self.cdf = None
-                self.lib.smcb_p2p_free(C.c_void_p(self._arena_local))
-                self._arena_local, self._arena_peers = None, []
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+class _P2PPool:
+    """Peer-mapped memory of one (process, process group): ONE mailbox and one (growing) arena per rank, allocated
+    and exchanged once -- a single tensor all-gather of the 64-byte CUDA IPC handles -- and then reused by every
+    sharded filter of the group: constructing the second ``ShardedSMC`` costs no collective, no
+    ``cudaIpcOpenMemHandle`` and no barrier.
+
+    Reuse is made safe by generations.  The mailbox has four slabs; filter number g of the group (all ranks make
+    their filters in the same order) uses slab g % 4 and zeroes -- locally, stream-ordered -- slab (g + 2) % 4.
+    Epochs inside a slab are step indices.  Nobody can still be writing into the slab being zeroed: it last served
+    generation g - 2, and this rank could only finish generation g - 1 after every peer had sent the statistics of
+    that filter's last step, i.e. after all their kernels of generation g - 2 had retired.  The arena (particles and
+    CDF of the exact global resampling) needs no tag: peers read it only inside a resampling step of the current
+    filter, and a rank finishes a filter only after every peer's reads of its last step are done."""
+
+    def __init__(self, ctx, world, rank, group):
+        self.ctx, self.lib, self.world, self.rank, self.group = ctx, ctx.lib, world, rank, group
+        self._mail = None          # [ptr per rank]
+        self._arena = None         # [ptr per rank]
+        self._arena_bytes = 0
+        self._gen = 0
+
+    def _exchange(self, nbytes):
+        """Allocate nbytes here (zeroed, synchronously), hand the IPC handle to every rank, map theirs."""
+        import torch.distributed as dist
+        ptr_ = C.c_void_p()
+        hbuf = C.create_string_buffer(64)
+        _lib.check(self.lib.smcb_p2p_alloc(self.ctx.handle, int(nbytes), C.byref(ptr_), hbuf))
+        mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(self.ctx.device)
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=self.ctx.device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh = allh.cpu().numpy().tobytes()
+        out = []
+        for r in range(self.world):
+            if r == self.rank:
+                out.append(ptr_.value)
+                continue
+            pp = C.c_void_p()
+            _lib.check(self.lib.smcb_p2p_open(self.ctx.handle, allh[64 * r:64 * (r + 1)], C.byref(pp)))
+            out.append(pp.value)
+        return out
+
+    def mailbox(self):
+        """[mailbox of rank r as mapped here] for the next filter of this group."""
+        nslab, slab = 4, 2 * self.world * 32 * 8
+        if self._mail is None:
+            self._mail = self._exchange(nslab * slab)
+        g = self._gen
+        self._gen += 1
+        tensor_from_ptr(self._mail[self.rank] + ((g + 2) % nslab) * slab, (slab // 8,), owner=self).zero_()
+        return [p + (g % nslab) * slab for p in self._mail]
+
+    def arena(self, nbytes):
+        if self._arena is None or nbytes > self._arena_bytes:
+            self._arena = self._exchange(nbytes)      # a smaller, earlier arena stays mapped until process exit
+            self._arena_bytes = nbytes
+        return self._arena[self.rank]
+
+    def arena_of(self, r):
+        return self._arena[r]
+
+
+_pools = {}
+
+
+def _p2p_pool(ctx, world, rank, group):
+    key = (ctx.device.index, id(group) if group is not None else None, world, rank)
+    if key not in _pools:
+        _pools[key] = _P2PPool(ctx, world, rank, group)
+    return _pools[key]
 
 
 class SMC:
@@ -262,6 +285,7 @@ class SMC:
         self.summaries = None if collect == "off" else collectors.Summaries(collect)
         self._seed = np.random.randint(0, 2 ** 31 - 1) if seed is None else int(seed)
         self._engine = None
+        self._dev_moments = False
         self._noise = noise
         spec = None
         if fused is not False:
@@ -272,7 +296,11 @@ class SMC:
             if spec is None and fused is True:
                 raise NotImplementedError("this Feynman-Kac model has no fused kernel")
         if spec is not None:
-            self._engine = _FusedEngine(spec, N, resampling, ESSrmin, self._seed, noise)
+            # collect=[Moments()] with the default mom_func: the step kernel accumulates sum w x / sum w x^2 next
+            # to its log-sum-exp triple and writes a (T, 8) table -- run() keeps its sync-free fast path
+            self._dev_moments = self.summaries is not None and self.summaries.device_moments(fk)
+            self._engine = _FusedEngine(spec, N, resampling, ESSrmin, self._seed, noise,
+                                        moments=self._dev_moments)
             self._row_cache = {}
         else:
             context().seed(self._seed)
@@ -486,7 +514,7 @@ class SMC:
         call, device work included (utils.timer semantics, utils.py:81-89)."""
         t0 = time.perf_counter()
         if self.fused and not self.verbose and not self.hist \
-                and (self.summaries is None or self.summaries.only_defaults) \
+                and (self.summaries is None or self.summaries.only_defaults or self._dev_moments) \
                 and getattr(getattr(type(self.fk), "done", None), "__qualname__", "") == "FeynmanKac.done":
             T = self._engine.T
             first = self.t
@@ -499,6 +527,8 @@ class SMC:
                 self.summaries._extend_defaults([float(v) for v in table[first:T, 0]],
                                                 [float(v) for v in table[first:T, 1]],
                                                 [bool(v) for v in table[first:T, 2]])
+                if self._dev_moments:
+                    self.summaries._extend_moments(self._engine.mom.cpu().numpy()[first:T], self._engine.dim)
         else:
             for _ in self:
                 pass

@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <new>
+
 #include "smcb_common.cuh"
 #include "smcb_math.cuh"
 #include "smcb_reduce.cuh"
@@ -40,6 +42,15 @@ extern "C" int smcb_create(smcb_ctx **out, int device, uint64_t seed) {
     SMCB_CUDA(cudaMalloc(&c->ws, c->ws_bytes));
     SMCB_CUDA(cudaMalloc(&c->counters, 64 * sizeof(unsigned int)));
     SMCB_CUDA(cudaMemset(c->counters, 0, 64 * sizeof(unsigned int)));
+    {   // lookup tables of the step kernels' elementary functions (long double on the host, once)
+        double *h = new (std::nothrow) double[kMathTabDoubles];
+        SMCB_REQUIRE(h != nullptr, "smcb_create: out of host memory");
+        fill_math_tables(h);
+        cudaError_t e = cudaMalloc(&c->math_tab, kMathTabBytes);
+        if (e == cudaSuccess) e = cudaMemcpy(c->math_tab, h, kMathTabBytes, cudaMemcpyHostToDevice);
+        delete[] h;
+        SMCB_CUDA(e);
+    }
     *out = c;
     return SMCB_OK;
 }
@@ -49,6 +60,7 @@ extern "C" int smcb_destroy(smcb_ctx *c) {
     cudaSetDevice(c->device);
     cudaFree(c->ws);
     cudaFree(c->counters);
+    cudaFree(c->math_tab);
     delete c;
     return SMCB_OK;
 }
@@ -887,24 +899,42 @@ extern "C" int smcb_mvnormal_logpdf(smcb_ctx *c, const double *x, const double *
 }
 
 // ---------------------------------------------------------------------------
-// test hook: evaluate the step kernel's fp64 elementary functions (smcb_math.cuh) on an array
-// fn: 0 fexp, 1 flog_pos, 2 sin(2 pi u), 3 cos(2 pi u)
+// test hook: evaluate the kernels' fp64 elementary functions (smcb_math.cuh) on an array
+// fn: 0 fexp, 1 flog_pos, 2 sin(2 pi u), 3 cos(2 pi u)            (polynomial family)
+//     4 texp, 5 tlog_pos, 6 sin(2 pi u), 7 cos(2 pi u), 8 tsqrt_pos (table family of the step kernels)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_device_math(int fn, const double *__restrict__ x,
-                                                       double *__restrict__ out, int64_t n) {
+                                                       double *__restrict__ out, int64_t n, const double *tab) {
+    __shared__ __align__(8) uint64_t s_bar;
+    if (fn >= 4) {
+        if (threadIdx.x == 0) mtab_issue(tab, &s_bar);
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+    }
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
         const double v = x[i];
         double r, s, c;
         if (fn == 0) r = fexp(v);
         else if (fn == 1) r = flog_pos(v);
-        else { fsincos2pi(v, s, c); r = (fn == 2) ? s : c; }
+        else if (fn == 2 || fn == 3) { fsincos2pi(v, s, c); r = (fn == 2) ? s : c; }
+        else if (fn == 4) r = texp(v);
+        else if (fn == 5) r = tlog_pos(v);
+        else if (fn == 8) r = tsqrt_pos(v);
+        else { tsincos2pi(v, s, c); r = (fn == 6) ? s : c; }
         out[i] = r;
     }
 }
 
 extern "C" int smcb_device_math(smcb_ctx *c, int fn, const double *x, double *out, int64_t n) {
-    SMCB_REQUIRE(c && x && out && n >= 1 && fn >= 0 && fn <= 3, "smcb_device_math: bad argument");
-    LAUNCH(c, k_device_math, grid_for(n, kBlock * 4), kBlock, fn, x, out, n);
+    SMCB_REQUIRE(c && x && out && n >= 1 && fn >= 0 && fn <= 8, "smcb_device_math: bad argument");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SMCB_CUDA(cudaFuncSetAttribute(k_device_math, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMathTabBytes));
+        attr_set = true;
+    }
+    k_device_math<<<grid_for(n, kBlock * 4), kBlock, fn >= 4 ? kMathTabBytes : 0, c->stream>>>(fn, x, out, n, c->math_tab);
+    c->launches++;
+    SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
 }

@@ -253,6 +253,7 @@ struct smcb_ctx {
     double *ws;             // workspace: partials / tile status
     size_t ws_bytes;
     unsigned int *counters; // "last block done" tickets (zeroed, self-resetting)
+    double *math_tab;       // smcb_tables.h (64 KB): exp / log / sincos tables of the step kernels
 };
 
 namespace smcb {

@@ -1,9 +1,9 @@
 // smcb_filter.cu -- host side of the fused filter (C-ABI entry points) + the 1-D model family.
-// The kernels live in smcb_filter_kernels.cuh; the d-dimensional models are instantiated in
+// The kernels live in smcb_step.cuh; the d-dimensional models are instantiated in
 // smcb_filter_nd.cu so that the two translation units compile in parallel.
 #include <stdlib.h>
 
-#include "smcb_filter_kernels.cuh"
+#include "smcb_step.cuh"
 
 int smcb_bind_nd(smcb_filter *f);      // smcb_filter_nd.cu
 int smcb_bind_1d_more(smcb_filter *f); // smcb_filter_1d.cu
@@ -45,13 +45,11 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     f->ctx = c;
     f->desc = *d;
     f->t_host = 0;
-    f->timed_ev = nullptr;
-    f->timed_kind = nullptr;
-    f->graph = nullptr; f->gexec = nullptr; f->has_graph = false; f->t_stop_host = 0;
-    f->scan_mem = nullptr;
+    f->timed = false;
+    f->mem = nullptr;
     const int rc = filter_setup(f, c, d);
     if (rc) {                       // nothing of a half-built filter survives an error
-        if (f->scan_mem) cudaFree(f->scan_mem);
+        if (f->mem) cudaFree(f->mem);
         delete f;
         return rc;
     }
@@ -59,25 +57,31 @@ extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_f
     return SMCB_OK;
 }
 
+static bool env_flag(const char *name, bool dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return v[0] != '0';
+}
+
 static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) {
     int rc = (d->dim == 1) ? smcb_bind_1d(f) : smcb_bind_nd(f);
     if (rc) return rc;
 
     const int64_t n = d->n;
-    const size_t sb1 = (scan_state_bytes(n) + 63) & ~(size_t)63;
-    const size_t sb2 = (scan_state_bytes(n + 1) + 63) & ~(size_t)63;
-    const size_t part = (size_t)kMaxGrid * 8 * sizeof(double);
-    char *mem;
-    const size_t tpb = (size_t)(kMaxGrid + 8) * sizeof(double);
-    constexpr size_t kHdr = 512;       // FilterDev, then the two "last block done" tickets
-    static_assert(sizeof(FilterDev) <= 448, "FilterDev outgrew its header slot");
-    SMCB_CUDA(cudaMalloc(&mem, kHdr + part + sb1 + sb2 + tpb + 64));
-    f->scan_mem = mem;
-    SMCB_CUDA(cudaMemsetAsync(mem, 0, kHdr + part, c->stream));
-    SMCB_CUDA(cudaMemsetAsync(mem + kHdr + part, 0xFF, sb1 + sb2, c->stream));
-    f->st = reinterpret_cast<FilterDev *>(mem);
+    constexpr size_t kHdr = 512;       // StepState[2] | grid-barrier counter | timeout flag
+    static_assert(2 * sizeof(StepState) <= 384, "StepState outgrew its header slot");
+    const size_t part = (size_t)2 * kMaxStepGrid * kPartStride * sizeof(double);
+    const size_t agg = (size_t)(kMaxStepGrid + 8) * sizeof(double);
+    SMCB_CUDA(cudaMalloc(&f->mem, kHdr + part + agg));
+    SMCB_CUDA(cudaMemsetAsync(f->mem, 0, kHdr + part + agg, c->stream));
     FilterArgs &a = f->args;
     memset(&a, 0, sizeof(a));
+    a.st = reinterpret_cast<StepState *>(f->mem);
+    a.bar = reinterpret_cast<unsigned long long *>(f->mem + 384);
+    a.sync_timeout = reinterpret_cast<int *>(f->mem + 392);
+    a.partials = reinterpret_cast<double *>(f->mem + kHdr);
+    a.blk_agg = reinterpret_cast<double *>(f->mem + kHdr + part);
+    a.math_tab = c->math_tab;
     a.X[0] = d->X[0]; a.X[1] = d->X[1]; a.lw[0] = d->lw[0]; a.lw[1] = d->lw[1];
     a.A = reinterpret_cast<long long *>(d->A);
     a.cdf = d->cdf;
@@ -87,214 +91,197 @@ static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) 
     a.data = d->data;
     a.sc = d->step_consts;
     a.summaries = d->summaries;
+    a.moments = d->moments;
     a.z_in = d->z_in; a.u_in = d->u_in;
-    a.st = f->st;
-    a.partials = reinterpret_cast<double *>(mem + kHdr);
-    a.ticket = reinterpret_cast<unsigned int *>(mem + 448);
-    a.ticket2 = reinterpret_cast<unsigned int *>(mem + 456);
-    char *sp = mem + kHdr + part;
-    a.scan.ticket = reinterpret_cast<unsigned int *>(sp);
-    a.scan.agg = reinterpret_cast<unsigned long long *>(sp + 16);
-    a.scan.cpref = a.scan.agg + scan_tiles(n);
-    sp += sb1;
-    a.scan2.ticket = reinterpret_cast<unsigned int *>(sp);
-    a.scan2.agg = reinterpret_cast<unsigned long long *>(sp + 16);
-    a.scan2.cpref = a.scan2.agg + scan_tiles(n + 1);
     a.dy = d->dy;
     a.n = n; a.n_global = d->n_global > 0 ? d->n_global : n;
     a.index_offset = d->index_offset; a.T = d->T;
     a.essrmin = d->essrmin;
     a.key = key_of(d->seed);
-    a.tile_pref = reinterpret_cast<double *>(mem + kHdr + part + sb1 + sb2);
-    {   // persistent grid: one wave of resident CTAs, each owning a contiguous range of pairs
+    {   // one CTA per SM, each owning a contiguous range of pairs; at least one pair per thread and CTA
         int dev = 0, sms = kSMs;
         SMCB_CUDA(cudaGetDevice(&dev));
         SMCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (const char *e = getenv("SMCB_SMS")) { int v = atoi(e); if (v >= 1 && v < sms) sms = v; }   // experiments
         const int64_t npairs = (n + 1) / 2;
-        const int64_t unit = (int64_t)kBlock * SMCB_KU;            // pairs per block iteration
-        int64_t g = (int64_t)sms * f->blocks_per_sm;
-        if (g > kMaxGrid) g = kMaxGrid;
-        int64_t chunk = ((npairs + g - 1) / g + unit - 1) / unit * unit;
+        int64_t g = sms < kMaxStepGrid ? sms : kMaxStepGrid;
+        const int64_t gmax = (npairs + f->block_size - 1) / f->block_size;
+        if (g > gmax) g = gmax;
+        if (g < 1) g = 1;
+        int64_t chunk = (npairs + g - 1) / g;
         g = (npairs + chunk - 1) / chunk;
         a.chunk = chunk;
-        f->grid_move = (int)(g < 1 ? 1 : g);
+        f->grid_move = (int)g;
         a.grid = f->grid_move;
-        a.world = d->world > 1 ? d->world : 1;
-        a.rank = d->world > 1 ? d->rank : 0;
-        a.local_stats = d->local_stats;
-        a.gathered = d->gathered;
-        a.mail_local = (a.world > 1) ? d->mail_local : nullptr;
-        for (int r = 0; r < 8; r++) a.mail_peer[r] = (a.world > 1 && r < a.world) ? d->mail_peer[r] : nullptr;
-        SMCB_REQUIRE(a.world == 1 || (a.rank >= 0 && a.rank < a.world), "smcb_filter_create: bad rank");
-        SMCB_REQUIRE(a.world == 1 || a.mail_local || (d->local_stats && d->gathered),
-                     "smcb_filter_create: world > 1 needs either a peer mailbox or local_stats / gathered");
-        if (a.mail_local) {
-            SMCB_REQUIRE(a.world <= 8, "smcb_filter_create: the peer mailbox supports at most 8 ranks");
-            for (int r = 0; r < a.world; r++)
-                SMCB_REQUIRE(a.mail_peer[r] != nullptr, "smcb_filter_create: mail_peer[%d] is NULL", r);
+    }
+    a.world = d->world > 1 ? d->world : 1;
+    a.rank = d->world > 1 ? d->rank : 0;
+    a.local_stats = d->local_stats;
+    a.gathered = d->gathered;
+    a.mail_local = (a.world > 1) ? d->mail_local : nullptr;
+    for (int r = 0; r < 8; r++) a.mail_peer[r] = (a.world > 1 && r < a.world) ? d->mail_peer[r] : nullptr;
+    SMCB_REQUIRE(a.world == 1 || (a.rank >= 0 && a.rank < a.world), "smcb_filter_create: bad rank");
+    SMCB_REQUIRE(a.world == 1 || a.mail_local || (d->local_stats && d->gathered),
+                 "smcb_filter_create: world > 1 needs either a peer mailbox or local_stats / gathered");
+    SMCB_REQUIRE(a.world <= 8, "smcb_filter_create: at most 8 ranks");
+    if (a.mail_local) {
+        for (int r = 0; r < a.world; r++)
+            SMCB_REQUIRE(a.mail_peer[r] != nullptr, "smcb_filter_create: mail_peer[%d] is NULL", r);
+    }
+    a.rs_global = (a.world > 1 && d->rs_global) ? 1 : 0;
+    if (a.rs_global) {
+        SMCB_REQUIRE(a.mail_local != nullptr, "smcb_filter_create: global resampling needs the peer mailbox");
+        SMCB_REQUIRE((n & 1) == 0, "smcb_filter_create: global resampling needs an even shard size");
+        if (d->scheme != SMCB_RS_SYSTEMATIC && d->scheme != SMCB_RS_STRATIFIED) {
+            set_error("fused filter: global resampling over shards supports systematic and stratified");
+            return SMCB_ENOSYS;
         }
-        a.rs_global = (a.world > 1 && d->rs_global) ? 1 : 0;
-        if (a.rs_global) {
-            SMCB_REQUIRE(a.mail_local != nullptr, "smcb_filter_create: global resampling needs the peer mailbox");
-            SMCB_REQUIRE((n & 1) == 0, "smcb_filter_create: global resampling needs an even shard size");
-            SMCB_REQUIRE(d->stage_X && d->stage_lw, "smcb_filter_create: global resampling needs stage_X / stage_lw");
-            if (d->fk == SMCB_FK_APF || d->fk == SMCB_FK_AUXBOOT) {
-                set_error("fused filter: global resampling over shards is built for Feynman-Kac kinds without "
-                          "auxiliary weights (bootstrap, guided)");
-                return SMCB_ENOSYS;
-            }
-            if (d->scheme != SMCB_RS_SYSTEMATIC && d->scheme != SMCB_RS_STRATIFIED) {
-                set_error("fused filter: global resampling over shards supports systematic and stratified");
-                return SMCB_ENOSYS;
-            }
-            a.stage_X = d->stage_X; a.stage_lw = d->stage_lw;
-            for (int r = 0; r < a.world; r++) {
-                SMCB_REQUIRE(d->peer_X0[r] && d->peer_X1[r] && d->peer_cdf[r],
-                             "smcb_filter_create: peer_X0 / peer_X1 / peer_cdf[%d] is NULL", r);
-                a.pX[r][0] = d->peer_X0[r]; a.pX[r][1] = d->peer_X1[r]; a.pcdf[r] = d->peer_cdf[r];
-            }
+        for (int r = 0; r < a.world; r++) {
+            SMCB_REQUIRE(d->peer_X0[r] && d->peer_X1[r] && d->peer_cdf[r],
+                         "smcb_filter_create: peer_X0 / peer_X1 / peer_cdf[%d] is NULL", r);
+            a.pX[r][0] = d->peer_X0[r]; a.pX[r][1] = d->peer_X1[r]; a.pcdf[r] = d->peer_cdf[r];
         }
     }
-    {
-        int64_t t2 = scan_tiles(n + 1);
-        f->grid_scan2 = (int)(t2 < kMaxGrid ? t2 : kMaxGrid);
-    }
-    // Optional: the whole step loop as ONE CUDA graph (WHILE + IF/ELSE conditional nodes, branch-
-    // specialised kernels).  Measured on this driver (profiles/graph_vs_loop.py) a conditional-node
-    // iteration costs ~7 us more than the two plain launches it replaces (14 -> 21 us per step at
-    // N = 1e3, 121 -> 130 us at N = 1e7), so the launch-per-step loop stays the default and the
-    // graph is opt-in (SMCB_GRAPH=1).
-    if (a.world == 1 && getenv("SMCB_GRAPH") != nullptr) {
-        if (f->build_graph(f) != SMCB_OK) {
-            cudaGetLastError();
-            f->has_graph = false;
-            set_error("");
-        }
-    }
+    // launch attributes: programmatic dependent launch hides the launch latency of step t+1 behind step t;
+    // a cooperative launch guarantees the co-residency the grid barrier of a resampling step relies on
+    // (the grid is one CTA per SM, so it is co-resident anyway unless another kernel occupies the device).
+    f->pdl = env_flag("SMCB_PDL", true);
+    f->coop = env_flag("SMCB_COOP", false);
     return SMCB_OK;
 }
 
 extern "C" int smcb_filter_destroy(smcb_filter *f) {
     if (!f) return SMCB_OK;
     cudaStreamSynchronize(f->ctx->stream);
-    if (f->gexec) cudaGraphExecDestroy(f->gexec);
-    if (f->graph) cudaGraphDestroy(f->graph);
-    cudaFree(f->scan_mem);
+    cudaFree(f->mem);
     delete f;
     return SMCB_OK;
 }
 
-// sharded filters: one step = step_local (kernels up to the per-rank statistics), an all-gather
-// of 8 doubles per rank done by the host layer (NCCL, same stream), then step_finish
+static int launch_one(smcb_filter *f) {
+    if (f->t_host >= f->desc.T) {
+        set_error("smcb_filter_step: all %lld steps already done (StopIteration)", (long long)f->desc.T);
+        return SMCB_EINVAL;
+    }
+    int rc = (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
+    if (rc && f->t_host > 0 && (f->pdl || f->coop)) {     // a launch attribute this driver rejects: plain launches
+        cudaGetLastError();
+        f->pdl = false; f->coop = false;
+        rc = f->launch_step(f);
+    }
+    if (rc) return rc;
+    f->t_host++;
+    return SMCB_OK;
+}
+
+// sharded filters with the host-driven exchange: one step = step_local (this rank's step kernel, then its
+// statistics in desc.local_stats), an all-gather of 16 doubles per rank done by the host layer (NCCL, same
+// stream), then step_finish (summaries of the step: global log-normaliser, ESS, logLt, next decision)
 extern "C" int smcb_filter_step_local(smcb_filter *f) {
-    SMCB_REQUIRE(f != nullptr && f->args.world > 1, "smcb_filter_step_local: not a sharded filter");
-    SMCB_REQUIRE(f->t_host < f->desc.T, "smcb_filter_step_local: all steps already done");
-    return (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
+    SMCB_REQUIRE(f != nullptr && f->args.world > 1 && f->args.mail_local == nullptr,
+                 "smcb_filter_step_local: not a sharded filter with the host-driven exchange");
+    int rc = launch_one(f);
+    if (rc) return rc;
+    return f->launch_publish(f);
 }
 
 extern "C" int smcb_filter_step_finish(smcb_filter *f) {
     SMCB_REQUIRE(f != nullptr && f->args.world > 1, "smcb_filter_step_finish: not a sharded filter");
-    int rc = f->launch_finish(f);
-    if (rc) return rc;
-    f->t_host++;
-    return SMCB_OK;
+    return f->launch_tail(f);
 }
 
 extern "C" int smcb_filter_step(smcb_filter *f, int64_t nsteps) {
     SMCB_REQUIRE(f != nullptr, "smcb_filter_step: NULL filter");
     SMCB_REQUIRE(f->args.world == 1 || f->args.mail_local != nullptr,
                  "smcb_filter_step: sharded filters without a peer mailbox use step_local / step_finish");
-    if (f->has_graph && nsteps > 0) {
-        SMCB_REQUIRE(f->t_host + nsteps <= f->desc.T, "smcb_filter_step: all %lld steps already done (StopIteration)",
-                     (long long)f->desc.T);
-        if (f->t_host == 0) {                      // step 0 (generate_particles) is a plain launch
-            int rc = f->launch_init(f);
-            if (rc) return rc;
-            f->t_host++;
-            nsteps--;
-        }
-        if (nsteps > 0) {                          // steps t_host .. t_host + nsteps - 1: ONE graph launch
-            f->t_stop_host = f->t_host + nsteps;
-            SMCB_CUDA(cudaMemcpyAsync(&f->st->t_stop, &f->t_stop_host, sizeof(long long), cudaMemcpyHostToDevice,
-                                      f->ctx->stream));
-            SMCB_CUDA(cudaGraphLaunch(f->gexec, f->ctx->stream));
-            f->ctx->launches += 2 * nsteps;        // k_cond + k_move per step (+1 scan per resampling step)
-            f->t_host += nsteps;
-        }
-        return SMCB_OK;
-    }
-    // host mirror of t: the device advances by exactly one per launched step
+    if (nsteps <= 0) return SMCB_OK;
+    // the device needs no host decision between steps: enqueue them all, then the tail that finalises the last
     for (int64_t i = 0; i < nsteps; i++) {
-        if (f->t_host >= f->desc.T) {
-            set_error("smcb_filter_step: all %lld steps already done (StopIteration)", (long long)f->desc.T);
-            return SMCB_EINVAL;
-        }
-        int rc = (f->t_host == 0) ? f->launch_init(f) : f->launch_step(f);
+        int rc = launch_one(f);
         if (rc) return rc;
-        if (f->args.world > 1 && (rc = f->launch_finish(f))) return rc;   // exchange happens on device
-        f->t_host++;
     }
-    return SMCB_OK;
+    return f->launch_tail(f);
 }
 
-// Same as smcb_filter_step, with a CUDA-event pair around every kernel launch (on the
-// launching stream).  out[0..3] = summed device milliseconds of {init, scan, spacings, move},
-// out[4..7] = number of launches of each.  Synchronises once, at the end.
+// Same as smcb_filter_step, with a CUDA-event pair around every kernel launch (on the launching stream, plain
+// serialised launches).  out[0..3] = summed device milliseconds of {init, step kernels of resampling steps,
+// tail, step kernels of non-resampling steps}, out[4..7] = number of launches of each.  Synchronises once.
 extern "C" int smcb_filter_step_timed(smcb_filter *f, int64_t nsteps, double *out8) {
     SMCB_REQUIRE(f && out8, "smcb_filter_step_timed: NULL argument");
-    SMCB_REQUIRE(nsteps >= 0 && nsteps <= 100000, "smcb_filter_step_timed: nsteps out of range");
+    SMCB_REQUIRE(nsteps >= 1 && nsteps <= 100000, "smcb_filter_step_timed: nsteps out of range");
     SMCB_REQUIRE(f->t_host + nsteps <= f->desc.T, "smcb_filter_step_timed: past the last step");
     SMCB_REQUIRE(f->args.world == 1, "smcb_filter_step_timed: single-device filters only");
     cudaStream_t s = f->ctx->stream;
-    const bool multi = f->desc.scheme == SMCB_RS_MULTINOMIAL;
-    const int per = multi ? 3 : 2;
-    const size_t nev = (size_t)nsteps * per * 2 + 2;
+    const size_t nev = (size_t)(nsteps + 1) * 2;
     cudaEvent_t *ev = new (std::nothrow) cudaEvent_t[nev];
-    SMCB_REQUIRE(ev != nullptr, "smcb_filter_step_timed: out of host memory");
-    for (size_t i = 0; i < nev; i++) SMCB_CUDA(cudaEventCreate(&ev[i]));
-    int *kind = new int[nev / 2];
-    size_t k = 0;
-    // re-implements launch_step with events in between: the kernels are the same objects
-    for (int64_t i = 0; i < nsteps; i++) {
-        if (f->t_host == 0) {
-            SMCB_CUDA(cudaEventRecord(ev[2 * k], s));
-            int rc = f->launch_init(f);
-            if (rc) return rc;
-            SMCB_CUDA(cudaEventRecord(ev[2 * k + 1], s));
-            kind[k++] = 0;
-        } else {
-            f->timed_ev = ev + 2 * k;
-            f->timed_kind = kind + k;
-            int rc = f->launch_step(f);
-            f->timed_ev = nullptr;
-            if (rc) return rc;
-            k += per;
+    double *rows = new (std::nothrow) double[(size_t)nsteps * SMCB_SUMMARY_STRIDE];
+    size_t made = 0;
+    int rc = SMCB_OK;
+    const int64_t t_first = f->t_host;
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error("smcb_filter_step_timed: %s -> %s", what, cudaGetErrorString(e));
+        rc = SMCB_ECUDA;
+    };
+    if (!ev || !rows) { set_error("smcb_filter_step_timed: out of host memory"); rc = SMCB_EINVAL; }
+    for (; rc == SMCB_OK && made < nev; made++) {
+        cudaError_t e = cudaEventCreate(&ev[made]);
+        if (e != cudaSuccess) { fail(e, "cudaEventCreate"); break; }
+    }
+    f->timed = true;
+    for (int64_t i = 0; rc == SMCB_OK && i <= nsteps; i++) {
+        cudaEventRecord(ev[2 * i], s);
+        rc = (i < nsteps) ? launch_one(f) : f->launch_tail(f);
+        cudaEventRecord(ev[2 * i + 1], s);
+    }
+    f->timed = false;
+    if (rc == SMCB_OK) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) fail(e, "cudaStreamSynchronize");
+    }
+    if (rc == SMCB_OK) {
+        cudaError_t e = cudaMemcpy(rows, f->args.summaries + (size_t)t_first * SMCB_SUMMARY_STRIDE,
+                                   sizeof(double) * nsteps * SMCB_SUMMARY_STRIDE, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) fail(e, "cudaMemcpy(summaries)");
+    }
+    if (rc == SMCB_OK) {
+        for (int j = 0; j < 8; j++) out8[j] = 0.0;
+        for (int64_t i = 0; i <= nsteps; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+            int kind = 2;                                            // tail
+            if (i < nsteps) {
+                const int64_t t = t_first + i;
+                kind = (t == 0) ? 0 : (rows[(size_t)i * SMCB_SUMMARY_STRIDE + 2] != 0.0 ? 1 : 3);
+            }
+            out8[kind] += ms;
+            out8[4 + kind] += 1.0;
         }
-        f->t_host++;
     }
-    SMCB_CUDA(cudaStreamSynchronize(s));
-    for (int j = 0; j < 8; j++) out8[j] = 0.0;
-    for (size_t i = 0; i < k; i++) {
-        float ms = 0.f;
-        SMCB_CUDA(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
-        out8[kind[i]] += ms;
-        out8[4 + kind[i]] += 1.0;
-    }
-    for (size_t i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    for (size_t i = 0; i < made; i++) cudaEventDestroy(ev[i]);
     delete[] ev;
-    delete[] kind;
-    return SMCB_OK;
+    delete[] rows;
+    return rc;
 }
 
 extern "C" int smcb_filter_state(smcb_filter *f, double *out8) {
     SMCB_REQUIRE(f && out8, "smcb_filter_state: NULL argument");
-    FilterDev h;
-    SMCB_CUDA(cudaMemcpyAsync(&h, f->st, sizeof(h), cudaMemcpyDeviceToHost, f->ctx->stream));
+    SMCB_REQUIRE(f->t_host >= 1, "smcb_filter_state: no step has run yet");
+    struct { StepState st[2]; char pad[384 - 2 * sizeof(StepState)]; unsigned long long bar; int timeout; int pad2; } h;
+    static_assert(sizeof(h) == 400, "header snapshot layout");
+    SMCB_CUDA(cudaMemcpyAsync(&h, f->mem, sizeof(h), cudaMemcpyDeviceToHost, f->ctx->stream));
     SMCB_CUDA(cudaStreamSynchronize(f->ctx->stream));
-    out8[0] = (double)h.t; out8[1] = (double)h.cur; out8[2] = (double)h.last_rs; out8[3] = h.logLt;
-    out8[4] = h.ess; out8[5] = h.log_mean_w; out8[6] = h.wm; out8[7] = h.ws;
-    if (h.sync_timeout) {
-        set_error("sharded filter: a wait on a peer GPU's flag timed out (a rank died or fell out of step)");
+    const StepState &s = h.st[(f->t_host - 1) & 1];
+    out8[0] = (double)(s.t + 1); out8[1] = (double)((f->t_host - 1) & 1); out8[2] = (double)s.rs; out8[3] = s.logLt;
+    out8[4] = s.ess; out8[5] = s.log_mean_w; out8[6] = s.wm; out8[7] = s.ws;
+    if (h.timeout) {
+        set_error(h.timeout == 2 ? "fused filter: the grid barrier of a resampling step timed out (the step kernel was "
+                                   "not co-resident: another kernel occupies the device)"
+                                 : "sharded filter: a wait on a peer GPU's flag timed out (a rank died or fell out of step)");
+        return SMCB_ECUDA;
+    }
+    if (s.t != f->t_host - 1) {
+        set_error("smcb_filter_state: the last step is not finalised (internal error: t=%lld, expected %lld)",
+                  (long long)s.t, (long long)(f->t_host - 1));
         return SMCB_ECUDA;
     }
     return SMCB_OK;
@@ -338,7 +325,7 @@ extern "C" int smcb_p2p_free(void *dev_ptr) {
 // debug builds only (profiles/build_variant.sh trace -DSMCB_TRACE): timeline of the last step-kernel launch
 extern "C" int smcb_debug_trace(unsigned long long *host_out, int n_words) {
     SMCB_CUDA(cudaDeviceSynchronize());
-    SMCB_CUDA(cudaMemcpyFromSymbol(host_out, smcb::g_trace, sizeof(unsigned long long) * n_words));
+    SMCB_CUDA(cudaMemcpyFromSymbol(host_out, smcb::g_trace, sizeof(unsigned long long) * (size_t)n_words));
     return SMCB_OK;
 }
 #endif

@@ -1,7 +1,7 @@
 // smcb_filter_1d.cu -- instantiations of the fused step kernels for the remaining 1-D stock models
 // (Gordon et al, ThetaLogistic, DiscreteCox, StochVolLeverage); a separate translation unit only so
-// that the library builds in parallel.  See smcb_filter_kernels.cuh.
-#include "smcb_filter_kernels.cuh"
+// that the library builds in parallel.  See smcb_step.cuh.
+#include "smcb_step.cuh"
 
 int smcb_bind_1d_more(smcb_filter *f) {
 #ifdef SMCB_BENCH_ONLY

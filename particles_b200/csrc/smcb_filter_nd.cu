@@ -1,6 +1,6 @@
 // smcb_filter_nd.cu -- instantiations of the fused step kernels for the d-dimensional models
-// (SoA state): BearingsOnly (d = 4) and MVLinearGauss (dx = 2..4).  See smcb_filter_kernels.cuh.
-#include "smcb_filter_kernels.cuh"
+// (SoA state): BearingsOnly (d = 4) and MVLinearGauss (dx = 2..4).  See smcb_step.cuh.
+#include "smcb_step.cuh"
 
 int smcb_bind_nd(smcb_filter *f) {
     const smcb_filter_desc *d = &f->desc;

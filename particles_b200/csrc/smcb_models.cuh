@@ -59,11 +59,11 @@ struct StochVolM {
     // Evaluated with ONE exp: z^2 = y^2 exp(-x) and log(exp(x/2)) = x/2 (differences of a few ulp
     // of the individual terms, < 1e-15 absolute; tolerance of the parity tests is 1e-10).
     __device__ __forceinline__ double obs_logpdf(const StepK &k, double, double x) const {
-        const double z2 = (k.y * k.y) * fexp(-x);
+        const double z2 = (k.y * k.y) * mexp(-x);
         return -0.5 * z2 - kHalfLog2Pi - 0.5 * x;
     }
     __device__ __forceinline__ double xhat(double xst, double sig, double yt) const {  // :475-476
-        return xst + 0.5 * (sig * sig) * ((yt * yt) * fexp(-xst) - 1.0);
+        return xst + 0.5 * (sig * sig) * ((yt * yt) * mexp(-xst) - 1.0);
     }
     __device__ __forceinline__ void prop0(const StepK &k, double &loc, double &scale, double &ls) const {
         loc = xhat(0.0, sig0, k.y); scale = sig0; ls = lsig0;     // :478-482
@@ -75,7 +75,7 @@ struct StochVolM {
     __device__ __forceinline__ double logeta(const StepK &k, double x) const {  // :490-498
         double xst = ext(x);
         double xstmmu = xst - mu;
-        double e = fexp(-xst);
+        double e = mexp(-xst);
         double xh = xst + 0.5 * (sigma * sigma) * ((k.y_next * k.y_next) * e - 1.0);
         double xhatmmu = xh - mu;
         return 0.5 / (sigma * sigma) * (xhatmmu * xhatmmu - xstmmu * xstmmu) -
@@ -161,7 +161,7 @@ struct ThetaLogisticM {
     }
     __device__ __forceinline__ void trans(const StepK &, double xp, double &loc, double &scale,
                                           double &ls) const {
-        loc = xp + tau0 - tau1 * fexp(tau2 * xp); scale = sX; ls = lsX;  // :675-678
+        loc = xp + tau0 - tau1 * mexp(tau2 * xp); scale = sX; ls = lsX;  // :675-678
     }
     __device__ __forceinline__ double obs_logpdf(const StepK &k, double, double x) const {
         return normal_logpdf_ls(k.y, x, sY, lsY);                 // :680-681
@@ -194,7 +194,7 @@ struct StochVolLevM {
     // PY = Normal(s phi u, s sqrt(1 - phi^2)), s = exp(x/2), u = innovation of X_t (:533-543)
     __device__ __forceinline__ double obs_logpdf(const StepK &k, double xp, double x) const {
         const double u = (k.t == 0) ? (x - mu) / sig0 : (x - (c0 + rho * xp)) / sigma;
-        const double s = fexp(0.5 * x);
+        const double s = mexp(0.5 * x);
         const double z = (k.y - s * phi * u) / (s * sq);
         return -z * z / 2.0 - kHalfLog2Pi - (0.5 * x + lsq);     // log(s * sq) = x/2 + log sq
     }
@@ -225,7 +225,7 @@ struct DiscreteCoxM {
     // Poisson(rate = e^x).logpmf(y) = xlogy(y, rate) - gammaln(y + 1) - rate, log(rate) = x
     __device__ __forceinline__ double obs_logpdf(const StepK &k, double, double x) const {
         const double xl = (k.y == 0.0) ? 0.0 : k.y * x;
-        return xl - k.sc0 - fexp(x);
+        return xl - k.sc0 - mexp(x);
     }
     __device__ __forceinline__ void prop0(const StepK &, double &, double &, double &) const {}
     __device__ __forceinline__ void prop(const StepK &, double, double &, double &, double &) const {}

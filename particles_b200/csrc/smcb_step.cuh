@@ -17,7 +17,7 @@
 //
 // The step index is a kernel argument (the host mirrors it); everything else a step needs from its
 // predecessor is in the partials (double-buffered by step parity) and in S_{t-2}.
-#include <cooperative_groups.h>
+#include <limits.h>
 #include <string.h>
 
 #include <new>
@@ -36,8 +36,19 @@ constexpr int kPartStride = 16;     // doubles per CTA partial row: w(m,s,q,-) a
 constexpr int kMailStride = 32;     // doubles per mailbox slot: the 16 above, then epochs
 constexpr int kMailEpoch = 16;      // slot[16] = t + 1 once the sender's statistics of step t are complete
 constexpr int kMailScan = 17;       // slot[17] = t + 1 once the sender's CDF of (resampling) step t is complete
-constexpr int kPer = (kMaxGrid + kBlock - 1) / kBlock;   // partial rows per thread in the prologue
+constexpr int kMaxStepGrid = 256;   // CTAs of the step kernel: ONE per SM (148 on a B200), each owning a contiguous range
 constexpr int kMaxD = 4;
+constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>= kMaxStepGrid: one partial row per thread)
+// threads per CTA of the step kernel.  One CTA per SM: the warp scheduler favours the oldest CTA / warps
+// (measured, profiles/r02a_variants_and_trace.json: with 3 equal CTAs per SM the first retired at 58 us, the
+// last at 89 us, the SM running 8 warps for the final third), so all warps of an SM live in one CTA and pace
+// each other (progress throttle in the streaming loop).
+template <class M> struct StepCfg {
+    static constexpr int BS = (M::D == 1) ? 768 : 512;
+    static constexpr int kStage = 4 * BS;             // doubles of CDF staged per output tile (2 BS outputs)
+    // dynamic shared memory: the math tables (smcb_tables.h, 64 KB), then two CDF slices
+    static constexpr size_t dyn_smem = kMathTabBytes + 2 * kStage * sizeof(double);
+};
 
 // S_t: what is known once step t is finalised; st[t & 1]
 struct StepState {
@@ -63,14 +74,15 @@ struct FilterArgs {
     const double *z_in, *u_in;
     StepState *st;           // [2]
     int *sync_timeout;       // a bounded wait expired (diagnostic; results are then invalid)
-    double *partials;        // [2][kMaxGrid][kPartStride]
+    double *partials;        // [2][kMaxStepGrid][kPartStride]
     unsigned long long *bar; // grid-barrier arrivals, never reset
     double *blk_agg;         // multinomial: per-CTA sums of the exponential spacings (grid + 1)
+    const double *math_tab;  // smcb_tables.h, built at context creation
     int64_t n, n_global, index_offset, T;
     int dy;
     int world, rank;
     int grid;
-    int64_t chunk;           // pairs of particles per block (blocked assignment, multiple of kBlock)
+    int64_t chunk;           // pairs of particles per CTA (contiguous ranges)
     double essrmin;
     Philox key;
     // sharded filters: host-driven exchange (NCCL all-gather of local_stats into gathered) ...
@@ -131,8 +143,8 @@ __device__ __forceinline__ double shift_factor(double m, double M) {
 // ---------------------------------------------------------------------------
 // block-wide fixed-order reductions; every thread receives the result
 // ---------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (kBlock/32) x NV */) {
+template <int NV, int BS>
+__device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (BS/32) x NV */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
@@ -151,7 +163,7 @@ __device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (
     for (int j = 0; j < NV; j++) {
         double m = smem[j];
 #pragma unroll
-        for (int w = 1; w < kBlock / 32; w++) {
+        for (int w = 1; w < BS / 32; w++) {
             const double o = smem[w * NV + j];
             m = (o > m || o != o) ? o : m;
         }
@@ -160,8 +172,8 @@ __device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (
     __syncthreads();
 }
 
-template <int NV>
-__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem /* (kBlock/32) x NV */) {
+template <int NV, int BS>
+__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem /* (BS/32) x NV */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
@@ -177,7 +189,7 @@ __device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem /* (
     for (int j = 0; j < NV; j++) {
         double s = smem[j];
 #pragma unroll
-        for (int w = 1; w < kBlock / 32; w++) s += smem[w * NV + j];
+        for (int w = 1; w < BS / 32; w++) s += smem[w * NV + j];
         v[j] = s;
     }
     __syncthreads();
@@ -208,7 +220,7 @@ __device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], 
 #pragma unroll
     for (int j = 1; j < NV; j++) mb = fmax(mb, v[j]);
     if (mb > a.w.m) {                       // also the first time (m = -inf): fexp(-inf) = 0
-        const double r = fexp_neg(a.w.m - mb);
+        const double r = texp_neg(a.w.m - mb);
         a.w.s *= r;
         a.w.q *= r * r;
         if (mom) {
@@ -220,7 +232,7 @@ __device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], 
     if (a.w.m == -CUDART_INF) return;       // nothing but -inf so far
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const double e = fexp_neg(v[j] - a.w.m);
+        const double e = texp_neg(v[j] - a.w.m);
         a.w.s += e;
         a.w.q = fma(e, e, a.w.q);
         if (mom && v[j] != -CUDART_INF) {
@@ -235,18 +247,19 @@ __device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], 
 }
 
 struct StepSmem {
-    double red[(kBlock / 32) * 16];
+    double red[32 * 16];
+    int prog[32];
     double peer[8][kMailStride];
     double goff[9], gpi[8];
     double pref[2];
 };
 
 // this CTA's row of the partials of step t: block reduction of the thread accumulators
-template <int D, bool APF>
+template <int D, bool APF, int BS>
 __device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, const Acc<D> &acc, const Lse3 &aux,
                                               bool mom, StepSmem &sh) {
     double mx[2] = {acc.w.m, APF ? aux.m : -CUDART_INF};
-    block_max_all<2>(mx, sh.red);
+    block_max_all<2, BS>(mx, sh.red);
     const double ew = shift_factor(acc.w.m, mx[0]);
     const double ea = APF ? shift_factor(aux.m, mx[1]) : 0.0;
     double v[4 + 2 * D];
@@ -259,9 +272,9 @@ __device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, 
         v[4 + c] = mom ? acc.sx[c] * ew : 0.0;
         v[4 + D + c] = mom ? acc.sxx[c] * ew : 0.0;
     }
-    block_sum_all<4 + 2 * D>(v, sh.red);
+    block_sum_all<4 + 2 * D, BS>(v, sh.red);
     if (threadIdx.x == 0) {
-        double *p = a.partials + ((size_t)(t & 1) * kMaxGrid + blockIdx.x) * kPartStride;
+        double *p = a.partials + ((size_t)(t & 1) * kMaxStepGrid + blockIdx.x) * kPartStride;
         p[0] = mx[0]; p[1] = v[0]; p[2] = v[1]; p[3] = 0.0;
         p[4] = APF ? mx[1] : mx[0]; p[5] = APF ? v[2] : v[0]; p[6] = APF ? v[3] : v[1]; p[7] = 0.0;
 #pragma unroll
@@ -289,6 +302,65 @@ __device__ __forceinline__ void merge16(double (&a)[16], const double *b) {
     }
 }
 
+// this shard's statistics of step s from the per-CTA partial rows (mailbox layout, 16 doubles): thread b owns
+// row b; fixed-order block reductions, so every CTA that runs this holds identical bits.  xrow = this thread's
+// (aux max, aux sum) for the CDF prefix.
+template <bool APF, int BS>
+__device__ __forceinline__ void shard_totals(const FilterArgs &a, long long s, bool mom, StepSmem &sh, double (&loc)[16],
+                                             double &xm_row, double &xs_row) {
+    const int G = a.grid, tid = threadIdx.x;
+    const double *row = a.partials + ((size_t)(s & 1) * kMaxStepGrid + tid) * kPartStride;
+    double pm = -CUDART_INF, ps = 0.0, pq = 0.0, xm = -CUDART_INF, xs = 0.0, xq = 0.0;
+    if (tid < G) {
+        const double2 r0 = __ldcg(reinterpret_cast<const double2 *>(row));
+        pm = r0.x; ps = r0.y; pq = __ldcg(row + 2);
+        if (APF) {
+            const double2 r1 = __ldcg(reinterpret_cast<const double2 *>(row + 4));
+            xm = r1.x; xs = r1.y; xq = __ldcg(row + 6);
+        } else {
+            xm = pm; xs = ps; xq = pq;
+        }
+    }
+    double mx[2] = {pm, xm};
+    block_max_all<2, BS>(mx, sh.red);
+    double v[12];
+    const double ew = shift_factor(pm, mx[0]);
+    v[0] = ps * ew;
+    v[1] = pq * (ew * ew);
+    const double ea = APF ? shift_factor(xm, mx[1]) : 0.0;
+    v[2] = APF ? xs * ea : 0.0;
+    v[3] = APF ? xq * (ea * ea) : 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) v[4 + c] = (mom && tid < G) ? __ldcg(row + 8 + c) * ew : 0.0;
+    block_sum_all<12, BS>(v, sh.red);
+    loc[0] = mx[0]; loc[1] = v[0]; loc[2] = v[1]; loc[3] = 0.0;
+    loc[4] = APF ? mx[1] : mx[0]; loc[5] = APF ? v[2] : v[0]; loc[6] = APF ? v[3] : v[1]; loc[7] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) loc[8 + c] = v[4 + c];
+    xm_row = xm; xs_row = xs;
+}
+
+// exclusive prefixes P_b, P_{b+1} of this CTA over per-CTA values v (thread b holds v_b, 0 beyond the grid):
+// sequential per warp + monotone clamps, the same bits in every CTA
+template <int BS>
+__device__ __forceinline__ void cta_prefix(double v, StepSmem &sh, double &p_b, double &p_next) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double iw = warp_scan_monotone(v, lane);
+    if (lane == 31) sh.red[warp] = iw;
+    __syncthreads();
+    double woff = 0.0;
+    for (int w_ = 0; w_ < BS / 32; w_++)
+        if (w_ < warp) woff = woff + sh.red[w_];
+    const double incl = woff + iw;                      // P_{tid+1}
+    if (tid == 0 && blockIdx.x == 0) sh.pref[0] = 0.0;
+    if (tid + 1 == (int)blockIdx.x) sh.pref[0] = incl;
+    if (tid == (int)blockIdx.x) sh.pref[1] = incl;
+    __syncthreads();
+    p_b = sh.pref[0];
+    p_next = fmax(sh.pref[1], p_b);
+    __syncthreads();
+}
+
 struct StepDecision {
     int rs;                   // resample at step t
     long long nrs_prev;       // resampling steps before step t (grid-barrier epochs already passed)
@@ -298,72 +370,19 @@ struct StepDecision {
 };
 
 // compute_summaries of step s = t - 1 (core.py:351-367) + time_to_resample of step t (core.py:181-183),
-// by every CTA; `writer` CTAs also record S_s, the summary row and the moments row.
-template <bool APF>
+// by every CTA; the `writer` CTA also records S_s, the summary row and the moments row.
+template <bool APF, int BS>
 __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
                                                       bool need_prefix) {
     const long long s = t - 1;
-    const int G = a.grid, tid = threadIdx.x;
-    const double *part = a.partials + (size_t)(s & 1) * kMaxGrid * kPartStride;
-    const int b0 = tid * kPer;
+    const int tid = threadIdx.x;
     const bool mom = writer && (a.moments != nullptr || a.world > 1);
-    // rows b0 .. b0 + kPer - 1 of the partials (contiguous per thread: the prefix below needs that)
-    double pm[kPer], ps[kPer], pq[kPer], xm_[kPer], xs_[kPer], xq_[kPer];
-    double mx[2] = {-CUDART_INF, -CUDART_INF};
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        const int b = b0 + i;
-        pm[i] = -CUDART_INF; ps[i] = 0.0; pq[i] = 0.0; xm_[i] = -CUDART_INF; xs_[i] = 0.0; xq_[i] = 0.0;
-        if (b < G) {
-            const double4 r0 = __ldcg(reinterpret_cast<const double4 *>(part + (size_t)b * kPartStride));
-            pm[i] = r0.x; ps[i] = r0.y; pq[i] = r0.z;
-            if (APF) {
-                const double4 r1 = __ldcg(reinterpret_cast<const double4 *>(part + (size_t)b * kPartStride + 4));
-                xm_[i] = r1.x; xs_[i] = r1.y; xq_[i] = r1.z;
-            } else {
-                xm_[i] = pm[i]; xs_[i] = ps[i]; xq_[i] = pq[i];
-            }
-            mx[0] = (pm[i] > mx[0] || pm[i] != pm[i]) ? pm[i] : mx[0];
-            mx[1] = (xm_[i] > mx[1] || xm_[i] != xm_[i]) ? xm_[i] : mx[1];
-        }
-    }
-    block_max_all<2>(mx, sh.red);
-    double loc[16];                                   // this shard's statistics, mailbox layout
-    {
-        double v[12];
-#pragma unroll
-        for (int j = 0; j < 12; j++) v[j] = 0.0;
-#pragma unroll
-        for (int i = 0; i < kPer; i++) {
-            const int b = b0 + i;
-            if (b < G) {
-                const double ew = shift_factor(pm[i], mx[0]);
-                v[0] += ps[i] * ew;
-                v[1] += pq[i] * (ew * ew);
-                if (APF) {
-                    const double ea = shift_factor(xm_[i], mx[1]);
-                    v[2] += xs_[i] * ea;
-                    v[3] += xq_[i] * (ea * ea);
-                }
-                if (mom) {
-                    const double *r = part + (size_t)b * kPartStride + 8;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) v[4 + c] += __ldcg(r + c) * ew;
-                }
-            }
-        }
-        block_sum_all<12>(v, sh.red);
-        loc[0] = mx[0]; loc[1] = v[0]; loc[2] = v[1]; loc[3] = 0.0;
-        loc[4] = APF ? mx[1] : mx[0]; loc[5] = APF ? v[2] : v[0]; loc[6] = APF ? v[3] : v[1]; loc[7] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; c++) loc[8 + c] = v[4 + c];
-    }
+    double loc[16], xm_row, xs_row;
+    shard_totals<APF, BS>(a, s, mom, sh, loc, xm_row, xs_row);
     double glob[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) glob[j] = loc[j];
     if (a.world > 1) {
-        const double *gath = a.gathered;
-        int gstride = 16;
         if (a.mail_local != nullptr) {
             // fused exchange over NVLink peer memory: CTA 0 stores this shard's statistics of step s into every
             // peer's mailbox (one lane per peer), fences, raises the epoch; every CTA waits for `world` epochs
@@ -380,12 +399,10 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
                 for (int i = 0; i < 16; i++)
                     sh.peer[tid][i] = *reinterpret_cast<const volatile double *>(box + (size_t)tid * kMailStride + i);
             }
-            __syncthreads();
-        } else {
-            if (tid < a.world)
-                for (int i = 0; i < 16; i++) sh.peer[tid][i] = __ldcg(gath + (size_t)tid * gstride + i);
-            __syncthreads();
+        } else if (tid < a.world) {
+            for (int i = 0; i < 16; i++) sh.peer[tid][i] = __ldcg(a.gathered + (size_t)tid * 16 + i);
         }
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < 16; j++) glob[j] = sh.peer[0][j];
         for (int r = 1; r < a.world; r++) merge16(glob, sh.peer[r]);         // rank order: identical bits everywhere
@@ -405,7 +422,13 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
     }
     const Lse3 w{glob[0], glob[1], glob[2]}, x{glob[4], glob[5], glob[6]};
     const Lse3 xl{loc[4], loc[5], loc[6]};
-    const StepState prev = (s >= 1) ? a.st[(s - 1) & 1] : StepState{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1, 0, 0, 0, {0, 0}};
+    StepState prev;
+    prev.logLt = 0.0; prev.log_mean_w = 0.0; prev.nrs = 0; prev.rs_next = 0;
+    if (s >= 1) {
+        const StepState *pp = a.st + ((s - 1) & 1);
+        prev.logLt = __ldcg(&pp->logLt); prev.log_mean_w = __ldcg(&pp->log_mean_w);
+        prev.nrs = __ldcg(&pp->nrs); prev.rs_next = __ldcg(&pp->rs_next);
+    }
     const double N = (double)a.n_global;
     double log_mean, ess, lm_aux, ess_aux;
     weights_scalars(w, N, log_mean, ess);
@@ -447,81 +470,63 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
         }
     }
     if (d.rs && need_prefix) {
-        // The CTAs own contiguous particle ranges, so their partial sums ARE the tile aggregates of the
-        // weight scan: exclusive prefixes P_0 = 0 <= P_1 <= ... <= P_G (fixed order, monotone, the same bits
-        // in every CTA), and the scan needs no look-back at all.
-        double run = 0.0, lc[kPer];
-#pragma unroll
-        for (int i = 0; i < kPer; i++) {
-            const int b = b0 + i;
-            double v = 0.0;
-            if (b < G) v = xs_[i] * shift_factor(xm_[i], d.xm) / d.xs;
-            run = run + v;
-            lc[i] = run;
-        }
-        const int lane = tid & 31, warp = tid >> 5;
-        const double iw = warp_scan_monotone(run, lane);
-        if (lane == 31) sh.red[warp] = iw;
-        __syncthreads();
-        double woff = 0.0;
-        for (int w_ = 0; w_ < kBlock / 32; w_++)
-            if (w_ < warp) woff = woff + sh.red[w_];
-        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
-        const double excl = (lane == 0) ? woff : (woff + up);
-        const double cap = woff + iw;
-        if (tid == 0 && blockIdx.x == 0) sh.pref[0] = 0.0;
-#pragma unroll
-        for (int i = 0; i < kPer; i++) {
-            const int b = b0 + i;                       // row b gives P_{b+1}
-            if (b < G) {
-                const double p = fmin(excl + lc[i], cap);
-                if (b + 1 == (int)blockIdx.x) sh.pref[0] = p;
-                if (b == (int)blockIdx.x) sh.pref[1] = p;
-            }
-        }
-        __syncthreads();
-        d.p_b = sh.pref[0];
-        d.p_next = sh.pref[1];
-        __syncthreads();
+        // The CTAs own contiguous particle ranges, so their partial sums ARE the tile aggregates of the weight
+        // scan: exclusive prefixes P_0 = 0 <= P_1 <= ... <= P_G (fixed order, monotone, the same bits in every
+        // CTA), and the scan needs no look-back at all.
+        const double v = (tid < a.grid) ? xs_row * shift_factor(xm_row, d.xm) / d.xs : 0.0;
+        cta_prefix<BS>(v, sh, d.p_b, d.p_next);
     }
     return d;
 }
 
-// all CTAs of the (co-resident, cooperative) grid have arrived `epoch` times
+// all CTAs of the (co-resident) grid have arrived; `target` = arrivals expected in total since the filter was made
 __device__ __forceinline__ void grid_barrier(const FilterArgs &a, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
         atomicAdd(a.bar, 1ull);
         const long long t0 = clock64();
         while (*reinterpret_cast<volatile unsigned long long *>(a.bar) < target) {
             if (clock64() - t0 > 8000000000ll) { *a.sync_timeout = 2; break; }
         }
         __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");     // the CDF is read by TMA (async proxy) next
     }
     __syncthreads();
+}
+
+// the range of pairs this CTA owns
+__device__ __forceinline__ void cta_range(const FilterArgs &a, int64_t &pstart, int64_t &pend) {
+    const int64_t npairs = (a.n + 1) >> 1;
+    pstart = (int64_t)blockIdx.x * a.chunk;
+    pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+    if (pstart > npairs) pstart = npairs;
 }
 
 // ---------------------------------------------------------------------------
 // t = 0: generate_particles + reweight (core.py:315-324, 373-374)
 // ---------------------------------------------------------------------------
 template <class M, int FK>
-__global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
+__global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_init(M model, FilterArgs a) {
     constexpr bool APF = FkTraits<FK>::apf;
-    constexpr int D = M::D, NZ = M::NZ;
+    constexpr int D = M::D, NZ = M::NZ, BS = StepCfg<M>::BS;
     __shared__ StepSmem sh;
+    __shared__ __align__(8) uint64_t s_tabbar;
+    if (threadIdx.x == 0) mtab_issue(a.math_tab, &s_tabbar);
+    __syncthreads();
+    mbar_wait(&s_tabbar, 0);
     const StepK k = step_consts(a, 0);
     double *Xo = a.X[0], *lwo = a.lw[0];
     Acc<D> acc;
     acc_init(acc);
     Lse3 aux = lse3_empty();
     const bool mom = a.moments != nullptr || a.world > 1;
-    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const int64_t n = a.n;
     const bool has_next = APF && a.T > 1;
-    const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
-    const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
-    for (int64_t p = pstart + threadIdx.x; p < pend; p += kBlock) {
+    const bool vec_x = (D == 1) || ((n & 1) == 0);
+    int64_t pstart, pend;
+    cta_range(a, pstart, pend);
+    for (int64_t p = pstart + threadIdx.x; p < pend; p += BS) {
         double z[2][NZ], x[2][D], l[2], av[2];
 #pragma unroll
         for (int c = 0; c < NZ; c++) {
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
                 z[0][c] = zz[2 * p];
                 z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
             } else {
-                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, (uint32_t)c, z[0][c], z[1][c]);
+                normal_pair_tab(a.key, (uint64_t)((a.index_offset >> 1) + p), 0u, (uint32_t)c, z[0][c], z[1][c]);
             }
         }
 #pragma unroll
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
             av[j] = has_next ? fix_nan(l[j] + model_logeta<M>(model, k, x[j])) : -CUDART_INF;
         }
         if (2 * p + 1 < n) {
-            if ((n & 1) == 0 || D == 1) {
+            if (vec_x) {
 #pragma unroll
                 for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
             } else {                                      // odd SoA stride: component rows are only 8-byte aligned
@@ -551,14 +556,14 @@ __global__ void __launch_bounds__(kBlock) k_init(M model, FilterArgs a) {
             st2(lwo + 2 * p, l[0], l[1]);
         } else {
 #pragma unroll
-            for (int c = 0; c < D; c++) Xo[(size_t)c * n + 2 * p] = x[0][c];
+            for (int c = 0; c < D; c++) { Xo[(size_t)c * n + 2 * p] = x[0][c]; x[1][c] = 0.0; }
             lwo[2 * p] = l[0];
             l[1] = -CUDART_INF; av[1] = -CUDART_INF;   // masked slot contributes exactly 0
         }
         acc_add_batch<2, D>(acc, l, x, mom);
         if (APF) lse3_add_batch<2>(aux, av);
     }
-    write_partial<D, APF>(a, 0, acc, aux, mom, sh);
+    write_partial<D, APF, BS>(a, 0, acc, aux, mom, sh);
 }
 
 // ---------------------------------------------------------------------------
@@ -608,32 +613,20 @@ struct LoadWeights {
         for (int j = 0; j < 8; j++) {
             double e = l[j];
             if (APF) e = fix_nan(e + model_logeta<M>(model, kprev, x[j]));
-            v[j] = (i0 + j < n) ? fexp(e - m) / s : 0.0;
+            v[j] = (i0 + j < n) ? texp(e - m) / s : 0.0;
         }
     }
 };
 
-// this CTA scans the particles it owns, [2 b chunk, 2 (b+1) chunk), from the exclusive prefix P_b the
-// prologue derived from the previous step's partial sums; every value is clamped into [P_b, P_{b+1}], so the
-// CDF is non-decreasing across CTAs by construction
-template <class M, int FK>
-__device__ __forceinline__ void scan_own_range(const M &model, const FilterArgs &a, long long t, int cur,
-                                               const StepDecision &d, double *s_warp) {
-    LoadWeights<M, FK> load;
-    load.lw = a.lw[cur];
-    load.X = a.X[cur];
-    load.ntot = a.n;
-    load.m = d.xm;
-    load.s = d.xs;
-    load.model = model;
-    load.kprev = step_consts(a, t - 1);
-    const int64_t n = a.n;
-    const int64_t e0 = 2 * (int64_t)blockIdx.x * a.chunk;
-    const int64_t e1 = e0 + 2 * a.chunk < n ? e0 + 2 * a.chunk : n;
-    const double p_b = d.p_b, p_next = d.p_next;
+// inclusive scan of the values load() yields on [e0, e1), written to out[]; starts from p_b and every value is
+// clamped into [p_b, p_next], so the result is non-decreasing across CTAs by construction
+template <int BS, class LOAD>
+__device__ __forceinline__ void scan_range(const LOAD &load, int64_t e0, int64_t e1, double p_b, double p_next,
+                                           double *out, double *s_warp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kTile = BS * kScanItems;
     double carry = 0.0;
-    for (int64_t base0 = e0; base0 < e1; base0 += kScanTile) {
+    for (int64_t base0 = e0; base0 < e1; base0 += kTile) {
         const int64_t i0 = base0 + (int64_t)tid * kScanItems;
         double r[kScanItems];
         load(i0, e1, r);
@@ -644,14 +637,14 @@ __device__ __forceinline__ void scan_own_range(const M &model, const FilterArgs 
         __syncthreads();
         double woff = 0.0, total = 0.0;
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) {
+        for (int w = 0; w < BS / 32; w++) {
             if (w < warp) woff = woff + s_warp[w];
             total = total + s_warp[w];
         }
         const double incl = woff + iw;
         const double up = __shfl_up_sync(0xffffffffu, iw, 1);
         const double excl = (lane == 0) ? woff : (woff + up);
-        const double b_i = p_b + carry;                       // base of this sub-tile
+        const double b_i = fmin(p_b + carry, p_next);         // base of this sub-tile
         const double carry_next = carry + total;
         const double b_next = fmin(p_b + carry_next, p_next); // base of the next one
         const double tb = b_i + excl;
@@ -660,11 +653,11 @@ __device__ __forceinline__ void scan_own_range(const M &model, const FilterArgs 
 #pragma unroll
         for (int j = 0; j < kScanItems; j++) o[j] = fmin(tb + r[j], cap);
         if (i0 + kScanItems <= e1) {
-            store_items(a.cdf, i0, o);
+            store_items(out, i0, o);
         } else {
 #pragma unroll
             for (int j = 0; j < kScanItems; j++)
-                if (i0 + j < e1) a.cdf[i0 + j] = o[j];
+                if (i0 + j < e1) out[i0 + j] = o[j];
         }
         carry = carry_next;
         __syncthreads();
@@ -675,19 +668,28 @@ __device__ __forceinline__ void scan_own_range(const M &model, const FilterArgs 
 // the weights: pass 1 leaves v_i = -log u_i in su[] and the CTA's sum in blk_agg[]; after a grid barrier
 // pass 2 scans the CTA's range from the (fixed-order, monotone) prefix of the CTA sums.
 __device__ __forceinline__ void spacings_range(const FilterArgs &a, int64_t &e0, int64_t &e1) {
-    const int64_t n1 = a.n + 1;
-    e0 = 2 * (int64_t)blockIdx.x * a.chunk;
-    e1 = e0 + 2 * a.chunk;
-    if (blockIdx.x == gridDim.x - 1 || e1 > n1) e1 = n1;          // the last CTA also takes element n
-    if (e0 > n1) e0 = n1;
+    int64_t pstart, pend;
+    cta_range(a, pstart, pend);
+    e0 = 2 * pstart;
+    e1 = 2 * pend < a.n ? 2 * pend : a.n;
+    if (blockIdx.x == gridDim.x - 1) e1 = a.n + 1;                // the last CTA also takes element n
 }
 
+struct LoadSpacings {
+    const double *su;
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (i0 + j < n) ? __ldcg(su + i0 + j) : 0.0;
+    }
+};
+
+template <int BS>
 __device__ __forceinline__ void spacings_pass1(const FilterArgs &a, long long t, StepSmem &sh) {
     int64_t e0, e1;
     spacings_range(a, e0, e1);
     const double *uin = a.u_in ? a.u_in + (size_t)t * (a.n + 1) : nullptr;
     double acc[1] = {0.0};
-    for (int64_t i = e0 + 2 * (int64_t)threadIdx.x; i < e1; i += 2 * kBlock) {
+    for (int64_t i = e0 + 2 * (int64_t)threadIdx.x; i < e1; i += 2 * BS) {
         double u0, u1;
         if (uin) { u0 = uin[i]; u1 = (i + 1 < e1) ? uin[i + 1] : 1.0; }
         else uniform_pair(a.key, (uint64_t)(i >> 1), (uint32_t)t, kPurposeUniform, u0, u1);
@@ -697,77 +699,19 @@ __device__ __forceinline__ void spacings_pass1(const FilterArgs &a, long long t,
         if (i + 1 < e1) a.su[i + 1] = v1;
         acc[0] += v0 + v1;
     }
-    block_sum_all<1>(acc, sh.red);
+    block_sum_all<1, BS>(acc, sh.red);
     if (threadIdx.x == 0) a.blk_agg[blockIdx.x] = acc[0];
 }
 
+template <int BS>
 __device__ __forceinline__ void spacings_pass2(const FilterArgs &a, StepSmem &sh, double *s_warp) {
-    // prefix of the CTA sums: every CTA runs the same sequential-per-thread + monotone block scan
-    const int G = a.grid, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b0 = tid * kPer;
-    double run = 0.0, lc[kPer];
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        const int b = b0 + i;
-        const double v = (b < G) ? __ldcg(a.blk_agg + b) : 0.0;
-        run = run + v;
-        lc[i] = run;
-    }
-    const double iw0 = warp_scan_monotone(run, lane);
-    if (lane == 31) sh.red[warp] = iw0;
-    __syncthreads();
-    double woff0 = 0.0;
-    for (int w_ = 0; w_ < kBlock / 32; w_++)
-        if (w_ < warp) woff0 = woff0 + sh.red[w_];
-    const double up0 = __shfl_up_sync(0xffffffffu, iw0, 1);
-    const double excl0 = (lane == 0) ? woff0 : (woff0 + up0);
-    const double cap0 = woff0 + iw0;
-    if (tid == 0 && blockIdx.x == 0) sh.pref[0] = 0.0;
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        const int b = b0 + i;
-        if (b < G) {
-            const double p = fmin(excl0 + lc[i], cap0);
-            if (b + 1 == (int)blockIdx.x) sh.pref[0] = p;
-            if (b == (int)blockIdx.x) sh.pref[1] = p;
-        }
-    }
-    __syncthreads();
-    const double p_b = sh.pref[0], p_next = sh.pref[1];
-    __syncthreads();
+    const double v = ((int)threadIdx.x < a.grid) ? __ldcg(a.blk_agg + threadIdx.x) : 0.0;
+    double p_b, p_next;
+    cta_prefix<BS>(v, sh, p_b, p_next);
     int64_t e0, e1;
     spacings_range(a, e0, e1);
-    double carry = 0.0;
-    for (int64_t base0 = e0; base0 < e1; base0 += kScanTile) {
-        const int64_t i0 = base0 + (int64_t)tid * kScanItems;
-        double r[kScanItems];
-#pragma unroll
-        for (int j = 0; j < kScanItems; j++) r[j] = (i0 + j < e1) ? a.su[i0 + j] : 0.0;
-#pragma unroll
-        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
-        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
-        if (lane == 31) s_warp[warp] = iw;
-        __syncthreads();
-        double woff = 0.0, total = 0.0;
-#pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) {
-            if (w < warp) woff = woff + s_warp[w];
-            total = total + s_warp[w];
-        }
-        const double incl = woff + iw;
-        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
-        const double excl = (lane == 0) ? woff : (woff + up);
-        const double b_i = p_b + carry;
-        const double carry_next = carry + total;
-        const double b_next = fmin(p_b + carry_next, p_next);
-        const double tb = b_i + excl;
-        const double cap = fmin(b_i + incl, b_next);
-#pragma unroll
-        for (int j = 0; j < kScanItems; j++)
-            if (i0 + j < e1) a.su[i0 + j] = fmin(tb + r[j], cap);
-        carry = carry_next;
-        __syncthreads();
-    }
+    LoadSpacings load{a.su};
+    scan_range<BS>(load, e0, e1, p_b, p_next, a.su, s_warp);
 }
 
 __device__ __forceinline__ int shard_of(const double *goff, const double *gpi, int world, double su) {
@@ -785,12 +729,13 @@ __device__ __forceinline__ int shard_of(const double *goff, const double *gpi, i
 #ifndef SMCB_KU
 #define SMCB_KU 2
 #endif
-#ifndef SMCB_MINB
-#define SMCB_MINB 3
+#ifndef SMCB_THROTTLE
+#define SMCB_THROTTLE 1          // iterations a warp may run ahead of the slowest warp of its CTA (0: off)
 #endif
 #ifdef SMCB_TRACE
-// per-CTA timeline of the LAST launch of the step kernel: {start, prologue done, main loop done, smid} in ns
-__device__ unsigned long long g_trace[4 * 2048];
+// per-CTA timeline of the LAST launch of the step kernel: {start, prologue done, main loop done, smid} in ns,
+// then per warp the time its main loop ended
+__device__ unsigned long long g_trace[4 * 256 + 32 * 256];
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -802,29 +747,36 @@ __device__ __forceinline__ unsigned int smid() {
     return r;
 }
 #define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[4 * blockIdx.x + (slot)] = gtimer(); } while (0)
+#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[4 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
 #else
 #define SMCB_TRACE_MARK(slot) do { } while (0)
+#define SMCB_TRACE_WARP() do { } while (0)
 #endif
 
 template <class M, int FK, int SCHEME>
-__global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M model, FilterArgs a, long long t) {
+__global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs a, long long t) {
     constexpr bool APF = FkTraits<FK>::apf;
-    constexpr int D = M::D, NZ = M::NZ;
-    constexpr int kStage = 2048;                       // doubles of CDF staged per output tile
+    constexpr int D = M::D, NZ = M::NZ, BS = StepCfg<M>::BS;
+    constexpr int kStage = StepCfg<M>::kStage;
+    extern __shared__ __align__(128) double s_dyn[];    // math tables | [2][kStage] CDF slices (resampling branch)
+    double *const s_stage = s_dyn + kMathTabDoubles;
     __shared__ StepSmem sh;
     __shared__ double s_su[2];
-    __shared__ __align__(128) double s_cdf2[2][kStage];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_tabbar;
     __shared__ long long s_hi;
-    __shared__ double s_warp[kBlock / 32];
+    __shared__ double s_warp[BS / 32];
 #ifdef SMCB_TRACE
     if (threadIdx.x == 0) { g_trace[4 * blockIdx.x] = gtimer(); g_trace[4 * blockIdx.x + 3] = smid(); }
 #endif
+    // the tables are constants: their copy may start before the previous kernel has retired
+    if (threadIdx.x == 0) mtab_issue(a.math_tab, &s_tabbar);
     // everything below reads what the previous kernel of the stream wrote (programmatic dependent launch:
     // this kernel may have been scheduled before its predecessor retired)
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
-    const StepDecision dec = step_prologue<APF>(a, t, sh, blockIdx.x == 0, true);
+    const StepDecision dec = step_prologue<APF, BS>(a, t, sh, blockIdx.x == 0, true);
+    mbar_wait(&s_tabbar, 0);                           // (the prologue's barriers made the init visible)
     SMCB_TRACE_MARK(1);
     const int cur = (int)((t - 1) & 1);                // step s writes buffers [s & 1]
     const bool rs = dec.rs != 0;
@@ -835,17 +787,19 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
     const double *__restrict__ lwi = a.lw[cur];
     double *__restrict__ Xo = a.X[cur ^ 1];
     double *__restrict__ lwo = a.lw[cur ^ 1];
-    const int64_t n = a.n, npairs = (n + 1) >> 1;
+    const int64_t n = a.n;
     const double *zin = a.z_in ? a.z_in + (size_t)t * NZ * n : nullptr;
     const bool last_apf = APF && (t + 1 < a.T);
     const bool mom = a.moments != nullptr || a.world > 1;
     const bool vec_x = (D == 1) || ((n & 1) == 0);     // SoA component rows are 16-byte aligned
+    int64_t pstart, pend;
+    cta_range(a, pstart, pend);
 
     Acc<D> acc;
     acc_init(acc);
     Lse3 aux = lse3_empty();
 
-    // propagate + reweight one pair of particles; writes x', lw'; returns lw' (and the auxiliary
+    // propagate + reweight one pair of particles; writes x', lw'; returns x', lw' (and the auxiliary
     // log-weights of the next step for an APF), -inf in masked slots
     auto do_pair = [&](int64_t p, const double (&xp)[2][D], const double (&base)[2], double (&x)[2][D], double *l,
                        double *av) {
@@ -857,7 +811,7 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                 z[0][c] = zz[2 * p];
                 z[1][c] = (2 * p + 1 < n) ? zz[2 * p + 1] : 0.0;
             } else {
-                normal_pair_fast(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, (uint32_t)c,
+                normal_pair_tab(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, (uint32_t)c,
                                  z[0][c], z[1][c]);
             }
         }
@@ -887,11 +841,16 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
     };
 
     if (!rs) {
-        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread
+        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread.  The warps
+        // of the CTA pace each other: none starts iteration i + SMCB_THROTTLE + 1 before all have finished i.
         constexpr int kU = SMCB_KU;
-        constexpr int64_t stride = kBlock;
-        const int64_t pstart = (int64_t)blockIdx.x * a.chunk;
-        const int64_t pend = pstart + a.chunk < npairs ? pstart + a.chunk : npairs;
+        constexpr int64_t stride = BS;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if SMCB_THROTTLE
+        if (threadIdx.x < 32) sh.prog[threadIdx.x] = (threadIdx.x < BS / 32) ? 0 : INT_MAX;
+        __syncthreads();
+        int it = 0;
+#endif
         for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kU * stride) {
             double xp[kU][2][D], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
 #pragma unroll
@@ -930,24 +889,44 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
             }
             acc_add_batch<2 * kU, D>(acc, l, x, mom);
             if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(aux, av);
+#if SMCB_THROTTLE
+            it++;
+            if (lane == 0) *reinterpret_cast<volatile int *>(&sh.prog[warp]) = it;
+            for (;;) {
+                const int mn = __reduce_min_sync(0xffffffffu, *reinterpret_cast<volatile int *>(&sh.prog[lane]));
+                if (mn >= it - SMCB_THROTTLE) break;
+                __nanosleep(100);
+            }
+#endif
         }
+#if SMCB_THROTTLE
+        if (lane == 0) *reinterpret_cast<volatile int *>(&sh.prog[warp]) = INT_MAX;    // done: nobody waits for this warp
+#endif
+        SMCB_TRACE_WARP();
     } else {
         // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
-        unsigned long long bar_target = (unsigned long long)gridDim.x *
-                                        ((unsigned long long)dec.nrs_prev * (SCHEME == SMCB_RS_MULTINOMIAL ? 2 : 1));
-        scan_own_range<M, FK>(model, a, t, cur, dec, s_warp);
+        constexpr int kBarriers = (SCHEME == SMCB_RS_MULTINOMIAL) ? 2 : 1;     // grid barriers per resampling step
+        unsigned long long bar_target = (unsigned long long)gridDim.x * ((unsigned long long)dec.nrs_prev * kBarriers);
+        {
+            LoadWeights<M, FK> load;
+            load.lw = a.lw[cur];
+            load.X = a.X[cur];
+            load.ntot = n;
+            load.m = dec.xm;
+            load.s = dec.xs;
+            load.model = model;
+            load.kprev = kprev;
+            const int64_t e1 = 2 * pend < n ? 2 * pend : n;
+            scan_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp);
+        }
         if (SCHEME == SMCB_RS_MULTINOMIAL) {
-            spacings_pass1(a, t, sh);
+            spacings_pass1<BS>(a, t, sh);
             bar_target += gridDim.x;
             grid_barrier(a, bar_target);
-            spacings_pass2(a, sh, s_warp);
+            spacings_pass2<BS>(a, sh, s_warp);
         }
         bar_target += gridDim.x;
         grid_barrier(a, bar_target);
-        const int64_t ntiles = (npairs + kBlock - 1) / kBlock;
-        const int64_t per = a.chunk / kBlock;                  // chunk is a multiple of kBlock
-        const int64_t tile_lo = (int64_t)blockIdx.x * per;
-        const int64_t tile_hi = tile_lo + per < ntiles ? tile_lo + per : ntiles;
         const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
         double u_sys = 0.0;
         if (SCHEME == SMCB_RS_SYSTEMATIC) {
@@ -991,20 +970,23 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                 const int64_t sb = lo_ & ~(int64_t)1;
                 const int c = (int)((n - sb) < kStage ? (n - sb) : kStage);
                 const uint32_t bytes = (uint32_t)(c & ~1) * 8u;
-                if (c & 1) s_cdf2[b][c - 1] = __ldcg(a.cdf + sb + c - 1);      // odd tail (n odd, end of the array)
+                double *dst = s_stage + (size_t)b * kStage;
+                if (c & 1) dst[c - 1] = __ldcg(a.cdf + sb + c - 1);      // odd tail (n odd, end of the array)
                 if (bytes) {
                     mbar_arrive_expect_tx(&s_bar[b], bytes);
-                    tma_bulk_g2s(&s_cdf2[b][0], a.cdf + sb, bytes, &s_bar[b]);
+                    tma_bulk_g2s(dst, a.cdf + sb, bytes, &s_bar[b]);
                 } else {
                     mbar_arrive(&s_bar[b]);
                 }
             };
-            for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
-                const int64_t p = tile * kBlock + threadIdx.x;
-                const int64_t k0 = 2 * tile * kBlock;
-                const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+            for (int64_t pbase = pstart; pbase < pend; pbase += BS) {
+                const int64_t p = pbase + threadIdx.x;
+                const bool active = p < pend;
+                const int64_t k0 = 2 * pbase;                                       // first / last output of the tile
+                const int64_t ptop = pbase + BS < pend ? pbase + BS : pend;
+                const int64_t k1 = (2 * ptop < n ? 2 * ptop : n) - 1;
                 double su[2] = {2.0, 2.0};
-                if (p < npairs) {
+                if (active) {
                     if (SCHEME == SMCB_RS_SYSTEMATIC) {                    // resampling.py:609
                         su[0] = (u_sys + (double)(2 * p)) / M_;
                         su[1] = (u_sys + (double)(2 * p + 1)) / M_;
@@ -1026,7 +1008,7 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                 __syncthreads();
                 const double su_first = s_su[0], su_last = s_su[1];
                 if (lo < 0) {                                      // first tile of this block
-                    lo = block_lower_bound<kBlock>(a.cdf, 0, n, su_first);
+                    lo = block_lower_bound<BS>(a.cdf, 0, n, su_first);
                     lo = lo < n - 1 ? lo : n - 1;
                     if (threadIdx.x == 0) issue(lo, buf);
                     __syncthreads();
@@ -1036,12 +1018,12 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                 const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
                 mbar_wait(&s_bar[buf], buf ? phase1 : phase0);
                 if (buf) phase1 ^= 1u; else phase0 ^= 1u;
-                const double *s_cdf = s_cdf2[buf];
+                const double *s_cdf = s_stage + (size_t)buf * kStage;
                 const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= su_last);
                 int64_t hi = lo;
-                if (!covered) hi = block_lower_bound<kBlock>(a.cdf, lo, n, su_last);   // rare: sparse mass
+                if (!covered) hi = block_lower_bound<BS>(a.cdf, lo, n, su_last);   // rare: sparse mass
                 int64_t a0 = 0, a1 = 0;
-                if (p < npairs) {
+                if (active) {
                     if (covered) {
                         int l0 = (int)(lo - sbase), h0 = cnt;
                         while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < su[0]) l0 = mid + 1; else h0 = mid; }
@@ -1060,14 +1042,14 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                         if (2 * p + 1 == k1) s_hi = a1;
                     } else {
                         const int64_t hi1 = hi < n ? hi + 1 : n;
-                        a0 = lower_bound(a.cdf, lo, hi1, su[0]);
-                        a1 = lower_bound(a.cdf, a0, hi1, su[1]);
+                        a0 = lower_bound_cg(a.cdf, lo, hi1, su[0]);
+                        a1 = lower_bound_cg(a.cdf, a0, hi1, su[1]);
                     }
                 }
                 __syncthreads();                                   // s_hi published; buffer buf^1 is free
                 const int64_t lo_next = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
-                if (tile + 1 < tile_hi && threadIdx.x == 0) issue(lo_next, buf ^ 1);
-                if (p < npairs) {
+                if (pbase + BS < pend && threadIdx.x == 0) issue(lo_next, buf ^ 1);
+                if (active) {
                     a0 = a0 < n - 1 ? a0 : n - 1;
                     a1 = a1 < n - 1 ? a1 : n - 1;
                     finish_pair(p, Xi, Xi, a0, a1, a0, a1);
@@ -1093,16 +1075,17 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
             __syncthreads();
             const int world = a.world;
             const double M_ = (double)a.n_global;
-            double *s_cdf = s_cdf2[0];
+            double *s_cdf = s_stage;
             int64_t lo = -1;
             int lo_shard = -1;
-            const int64_t npairs_e = n >> 1;                        // sharded filters have even n
-            for (int64_t tile = tile_lo; tile < tile_hi; tile++) {
-                const int64_t p = tile * kBlock + threadIdx.x;
-                const int64_t k0 = 2 * tile * kBlock;
-                const int64_t k1 = (k0 + 2 * kBlock < n ? k0 + 2 * kBlock : n) - 1;
+            for (int64_t pbase = pstart; pbase < pend; pbase += BS) {
+                const int64_t p = pbase + threadIdx.x;
+                const bool active = p < pend;                               // sharded filters have even n
+                const int64_t k0 = 2 * pbase;
+                const int64_t ptop = pbase + BS < pend ? pbase + BS : pend;
+                const int64_t k1 = 2 * ptop - 1;
                 double su[2] = {2.0, 2.0};
-                if (p < npairs_e) {
+                if (active) {
                     const double g0 = (double)(a.index_offset + 2 * p);
                     if (SCHEME == SMCB_RS_SYSTEMATIC) {
                         su[0] = (u_sys + g0) / M_;
@@ -1130,20 +1113,20 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                     const double off = sh.goff[kf], pi = sh.gpi[kf];
                     const double v0 = fmin((su[0] - off) / pi, 1.0), v1 = fmin((su[1] - off) / pi, 1.0);
                     const double v_first = fmin((su_first - off) / pi, 1.0), v_last = fmin((su_last - off) / pi, 1.0);
-                    if (lo < 0 || lo_shard != kf) lo = block_lower_bound<kBlock>(cdf, 0, n, v_first);
+                    if (lo < 0 || lo_shard != kf) lo = block_lower_bound<BS>(cdf, 0, n, v_first);
                     if (lo > n - 1) lo = n - 1;
                     lo_shard = kf;
                     const int64_t sbase = lo & ~(int64_t)1;
                     const int cnt = (int)((n - sbase) < kStage ? (n - sbase) : kStage);
-                    for (int i = 2 * threadIdx.x; i < cnt; i += 2 * kBlock) {
+                    for (int i = 2 * threadIdx.x; i < cnt; i += 2 * BS) {
                         if (i + 1 < cnt) *reinterpret_cast<double2 *>(&s_cdf[i]) = __ldcg(reinterpret_cast<const double2 *>(cdf + sbase + i));
                         else s_cdf[i] = __ldcg(cdf + sbase + i);
                     }
                     __syncthreads();
                     const bool covered = (sbase + cnt >= n) || (s_cdf[cnt - 1] >= v_last);
                     int64_t hi = lo;
-                    if (!covered) hi = block_lower_bound<kBlock>(cdf, lo, n, v_last);
-                    if (p < npairs_e) {
+                    if (!covered) hi = block_lower_bound<BS>(cdf, lo, n, v_last);
+                    if (active) {
                         if (covered) {
                             int l0 = (int)(lo - sbase), h0 = cnt;
                             while (l0 < h0) { const int mid = (l0 + h0) >> 1; if (s_cdf[mid] < v0) l0 = mid + 1; else h0 = mid; }
@@ -1159,25 +1142,25 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
                             if (2 * p + 1 == k1) s_hi = an[1];
                         } else {
                             const int64_t hi1 = hi < n ? hi + 1 : n;
-                            an[0] = lower_bound(cdf, lo, hi1, v0);
-                            an[1] = lower_bound(cdf, an[0], hi1, v1);
+                            an[0] = lower_bound_cg(cdf, lo, hi1, v0);
+                            an[1] = lower_bound_cg(cdf, an[0], hi1, v1);
                         }
                     }
                     __syncthreads();
                     lo = covered ? (s_hi < n ? s_hi : n - 1) : (hi < n ? hi : n - 1);
                 } else {
                     // the tile straddles a shard boundary (at most world - 1 tiles per rank): plain searches
-                    if (p < npairs_e) {
+                    if (active) {
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
                             ks[j] = shard_of(sh.goff, sh.gpi, world, su[j]);
                             const double v = fmin((su[j] - sh.goff[ks[j]]) / sh.gpi[ks[j]], 1.0);
-                            an[j] = lower_bound(a.pcdf[ks[j]], 0, n, v);
+                            an[j] = lower_bound_cg(a.pcdf[ks[j]], 0, n, v);
                         }
                     }
                     lo = -1;
                 }
-                if (p < npairs_e) {
+                if (active) {
                     const int64_t a0 = an[0] < n - 1 ? an[0] : n - 1, a1 = an[1] < n - 1 ? an[1] : n - 1;
                     // ancestors are GLOBAL particle indices
                     finish_pair(p, a.pX[ks[0]][cur], a.pX[ks[1]][cur], a0, a1, (long long)ks[0] * n + a0,
@@ -1188,65 +1171,25 @@ __global__ void __launch_bounds__(kBlock, (M::D == 1 ? SMCB_MINB : 2)) k_step(M 
         }
     }
     SMCB_TRACE_MARK(2);
-    write_partial<D, APF>(a, t, acc, aux, mom, sh);
+    write_partial<D, APF, BS>(a, t, acc, aux, mom, sh);
 }
 
 // the prologue alone (one CTA): finalises the last enqueued step so that the host can read its summaries
 template <bool APF>
-__global__ void __launch_bounds__(kBlock) k_tail(FilterArgs a, long long t) {
+__global__ void __launch_bounds__(kTailBlock) k_tail(FilterArgs a, long long t) {
     __shared__ StepSmem sh;
     cudaGridDependencySynchronize();
-    step_prologue<APF>(a, t, sh, true, false);
+    step_prologue<APF, kTailBlock>(a, t, sh, true, false);
 }
 
-// sharded filters with the host-driven exchange: this shard's statistics of step s -> local_stats
+// sharded filters with the host-driven exchange (NCCL): this shard's statistics of step s -> local_stats
 template <bool APF>
-__global__ void __launch_bounds__(kBlock) k_publish(FilterArgs a, long long s) {
+__global__ void __launch_bounds__(kTailBlock) k_publish(FilterArgs a, long long s) {
     __shared__ StepSmem sh;
-    FilterArgs b = a;
-    b.world = 1;                       // local merge only
-    b.moments = nullptr;
-    b.summaries = nullptr;
-    // reuse the prologue's fixed-order merge by running it on the local rows; it returns the shard totals
-    // through the partial row 0 of the OTHER parity?  No: keep it explicit and simple here.
-    const int G = a.grid, tid = threadIdx.x;
-    const double *part = a.partials + (size_t)(s & 1) * kMaxGrid * kPartStride;
-    const int b0 = tid * kPer;
-    double mx[2] = {-CUDART_INF, -CUDART_INF};
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        const int r = b0 + i;
-        if (r < G) {
-            const double m0 = __ldcg(part + (size_t)r * kPartStride), m1 = __ldcg(part + (size_t)r * kPartStride + 4);
-            mx[0] = (m0 > mx[0] || m0 != m0) ? m0 : mx[0];
-            mx[1] = (m1 > mx[1] || m1 != m1) ? m1 : mx[1];
-        }
-    }
-    block_max_all<2>(mx, sh.red);
-    double v[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) v[j] = 0.0;
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        const int r = b0 + i;
-        if (r < G) {
-            const double *row = part + (size_t)r * kPartStride;
-            const double ew = shift_factor(__ldcg(row), mx[0]), ea = shift_factor(__ldcg(row + 4), mx[1]);
-            v[0] += __ldcg(row + 1) * ew;
-            v[1] += __ldcg(row + 2) * (ew * ew);
-            v[2] += __ldcg(row + 5) * ea;
-            v[3] += __ldcg(row + 6) * (ea * ea);
-#pragma unroll
-            for (int c = 0; c < 8; c++) v[4 + c] += __ldcg(row + 8 + c) * ew;
-        }
-    }
-    block_sum_all<12>(v, sh.red);
-    if (tid == 0) {
-        double *o = a.local_stats;
-        o[0] = mx[0]; o[1] = v[0]; o[2] = v[1]; o[3] = 0.0;
-        o[4] = mx[1]; o[5] = v[2]; o[6] = v[3]; o[7] = 0.0;
-        for (int c = 0; c < 8; c++) o[8 + c] = v[4 + c];
-    }
+    double loc[16], xm_row, xs_row;
+    shard_totals<APF, kTailBlock>(a, s, true, sh, loc, xm_row, xs_row);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 16; i++) a.local_stats[i] = loc[i];
 }
 
 }  // namespace smcb
@@ -1259,11 +1202,12 @@ struct smcb_filter {
     smcb_filter_desc desc;
     FilterArgs args;
     char *mem;            // header (StepState[2], barrier, timeout flag) + partials + block aggregates
-    int grid_move;
-    int blocks_per_sm;    // resident CTAs/SM of the step kernel (persistent grid = SMs x this)
+    int grid_move;        // CTAs of the step kernel: one per SM (fewer for tiny N)
+    int block_size;       // threads per CTA of the step kernel
+    size_t dyn_smem;      // its dynamic shared memory (CDF staging buffers)
     int64_t t_host;       // steps launched so far (the device needs no other notion of time)
-    int64_t t_tail;       // the step count the last k_tail was launched for (-1: none)
     bool pdl, coop;       // launch attributes in use (programmatic dependent launch, cooperative)
+    bool timed;           // inside smcb_filter_step_timed: plain serialised launches
     int (*launch_init)(smcb_filter *);
     int (*launch_step)(smcb_filter *);
     int (*launch_tail)(smcb_filter *);
@@ -1271,16 +1215,21 @@ struct smcb_filter {
 };
 
 template <class... Args>
-static int launch_ex(smcb_filter *f, void (*kern)(Args...), int grid, bool coop, bool pdl, Args... args) {
+static int launch_ex(smcb_filter *f, void (*kern)(Args...), int grid, int block, size_t smem, bool coop, bool pdl,
+                     Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kBlock);
-    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = f->ctx->stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (coop) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; na++; }
-    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = na;
     SMCB_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
@@ -1292,14 +1241,15 @@ template <class M, int FK, int SCHEME>
 static int launch_step_t(smcb_filter *f) {
     M model;
     model.load(f->desc.params);
-    return launch_ex(f, k_step<M, FK, SCHEME>, f->grid_move, f->coop, f->pdl, model, f->args, (long long)f->t_host);
+    return launch_ex(f, k_step<M, FK, SCHEME>, f->grid_move, f->block_size, f->dyn_smem, f->coop,
+                     f->pdl && !f->timed, model, f->args, (long long)f->t_host);
 }
 
 template <class M, int FK>
 static int launch_init_t(smcb_filter *f) {
     M model;
     model.load(f->desc.params);
-    k_init<M, FK><<<f->grid_move, kBlock, 0, f->ctx->stream>>>(model, f->args);
+    k_init<M, FK><<<f->grid_move, f->block_size, kMathTabBytes, f->ctx->stream>>>(model, f->args);
     f->ctx->launches++;
     SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
@@ -1307,12 +1257,13 @@ static int launch_init_t(smcb_filter *f) {
 
 template <int FK>
 static int launch_tail_t(smcb_filter *f) {
-    return launch_ex(f, k_tail<FkTraits<FK>::apf>, 1, false, f->pdl, f->args, (long long)f->t_host);
+    return launch_ex(f, k_tail<FkTraits<FK>::apf>, 1, kTailBlock, 0, false, f->pdl && !f->timed, f->args,
+                     (long long)f->t_host);
 }
 
 template <int FK>
 static int launch_publish_t(smcb_filter *f) {
-    k_publish<FkTraits<FK>::apf><<<1, kBlock, 0, f->ctx->stream>>>(f->args, (long long)(f->t_host - 1));
+    k_publish<FkTraits<FK>::apf><<<1, kTailBlock, 0, f->ctx->stream>>>(f->args, (long long)(f->t_host - 1));
     f->ctx->launches++;
     SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
@@ -1324,9 +1275,18 @@ static int bind_one(smcb_filter *f) {
     f->launch_step = launch_step_t<M, FK, SCHEME>;
     f->launch_tail = launch_tail_t<FK>;
     f->launch_publish = launch_publish_t<FK>;
+    f->block_size = StepCfg<M>::BS;
+    f->dyn_smem = StepCfg<M>::dyn_smem;
+    SMCB_CUDA(cudaFuncSetAttribute(k_step<M, FK, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)StepCfg<M>::dyn_smem));
+    SMCB_CUDA(cudaFuncSetAttribute(k_init<M, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMathTabBytes));
     int nb = 0;
-    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step<M, FK, SCHEME>, kBlock, 0));
-    f->blocks_per_sm = nb < 1 ? 1 : nb;
+    SMCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_step<M, FK, SCHEME>, StepCfg<M>::BS,
+                                                            StepCfg<M>::dyn_smem));
+    if (nb < 1) {
+        set_error("fused filter: the step kernel does not fit on an SM of this device");
+        return SMCB_ECUDA;
+    }
     return SMCB_OK;
 }
 

@@ -95,12 +95,14 @@ class _RawDeviceBuffer:
     """Minimal ``__cuda_array_interface__`` carrier: lets torch view device memory it did not allocate
     (peer-mapped arenas from ``smcb_p2p_alloc``).  The owner keeps the allocation alive."""
 
-    def __init__(self, ptr, shape, typestr="<f8"):
+    def __init__(self, ptr, shape, typestr="<f8", owner=None):
+        self.owner = owner          # keeps the allocation's owner alive as long as a tensor views it
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2, "strides": None}
 
 
-def tensor_from_ptr(ptr, shape, dtype=torch.float64):
-    """A torch tensor over raw device memory (no copy, no ownership)."""
+def tensor_from_ptr(ptr, shape, dtype=torch.float64, owner=None):
+    """A torch tensor over raw device memory (no copy); `owner` is referenced by the tensor's base object so
+    that the allocation outlives every view handed out."""
     typestr = {torch.float64: "<f8", torch.int64: "<i8"}[dtype]
-    return torch.as_tensor(_RawDeviceBuffer(ptr, shape, typestr), device=context().device)
+    return torch.as_tensor(_RawDeviceBuffer(ptr, shape, typestr, owner), device=context().device)

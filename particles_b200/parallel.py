@@ -4,8 +4,8 @@ per GPU (``torch.distributed``, backend nccl), SURVEY.md section 8(e).
 Per step every rank runs the fused kernels on its own shard and the ranks exchange ONE
 message: an all-gather of 8 doubles per rank -- (max, sum exp, sum exp^2) of the shard's
 inferential and auxiliary log-weights.  Every rank then forms the same global
-log-normaliser, ESS, logLt increment and resampling decision (``k_finish`` in
-csrc/smcb_filter.cu merges the triples in rank order, so all ranks hold identical bits).
+log-normaliser, ESS, logLt increment and resampling decision (the prologue of the next step
+kernel, csrc/smcb_step.cuh, merges the triples in rank order, so all ranks hold identical bits).
 Resampling is per shard ("island" scheme): a shard resamples its own N/G particles from its
 own normalised weights and restarts them at log-weight  LSE_shard(aux) - LSE_all(w) + log G,
 i.e. the shard keeps its share of the total mass, which keeps the likelihood estimator

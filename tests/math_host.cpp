@@ -3,7 +3,9 @@
 // ALGORITHMS can be checked on the CPU against NumPy / mpmath and against the oracle
 // (tests/test_math_host.py, tests/test_models_host.py).  CUDA intrinsics are restated bit-for-bit below; compile with
 // -ffp-contract=off so that only the explicit fma() calls fuse, as nvcc -fmad=false does.
-//   g++ -O2 -ffp-contract=off -shared -fPIC [-DSMCB_TABLE_MATH=1] -I particles_b200/csrc tests/math_host.cpp
+//   g++ -O2 -ffp-contract=off -shared -fPIC -I particles_b200/csrc tests/math_host.cpp
+// Both families of smcb_math.cuh are exported: `tab` = 0 polynomial (stand-alone kernels), 1 table-assisted (step
+// kernels; the tables of smcb_tables.h are built here by the same host function the library uses).
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -48,7 +50,7 @@ static inline void philox4x32_10k(uint32_t, uint32_t, uint32_t, uint32_t, const 
 
 namespace {
 using namespace smcb;
-// same construction as step_consts() of smcb_filter_kernels.cuh
+// same construction as step_consts() of smcb_step.cuh
 StepK make_step(const double *data, long T, int dy, const double *sc, long t) {
     StepK k;
     k.t = t;
@@ -119,15 +121,28 @@ int mh_model_step(int model, int fk, int dim, const double *params, const double
     }
 }
 
-int mh_table_math() { return SMCB_TABLE_MATH; }
-void mh_exp(const double *x, double *y, long n, int kind) {
-    for (long i = 0; i < n; i++)
-        y[i] = kind == 0 ? smcb::fexp(x[i]) : (kind == 1 ? smcb::fexp_neg(x[i]) : smcb::fexp_mid(x[i]));
+static double g_tables[smcb::kMathTabDoubles];
+void mh_init() { smcb::fill_math_tables(g_tables); smcb::g_mtab_host = g_tables; }
+const double *mh_tables() { return g_tables; }
+int mh_table_doubles() { return smcb::kMathTabDoubles; }
+void mh_exp(const double *x, double *y, long n, int kind, int tab) {
+    for (long i = 0; i < n; i++) {
+        if (tab) y[i] = kind == 0 ? smcb::texp(x[i]) : smcb::texp_neg(x[i]);
+        else y[i] = kind == 0 ? smcb::fexp(x[i]) : (kind == 1 ? smcb::fexp_neg(x[i]) : smcb::fexp_mid(x[i]));
+    }
 }
-void mh_log(const double *x, double *y, long n) { for (long i = 0; i < n; i++) y[i] = smcb::flog_pos(x[i]); }
-void mh_sincos2pi(const double *u, double *s, double *c, long n) { for (long i = 0; i < n; i++) smcb::fsincos2pi(u[i], s[i], c[i]); }
-void mh_box_muller(const uint32_t *r, double *z, long npairs) {
-    for (long i = 0; i < npairs; i++) smcb::box_muller_fast(r + 4 * i, z[2 * i], z[2 * i + 1]);
+void mh_log(const double *x, double *y, long n, int tab) {
+    for (long i = 0; i < n; i++) y[i] = tab ? smcb::tlog_pos(x[i]) : smcb::flog_pos(x[i]);
+}
+void mh_sqrt(const double *x, double *y, long n) { for (long i = 0; i < n; i++) y[i] = smcb::tsqrt_pos(x[i]); }
+void mh_sincos2pi(const double *u, double *s, double *c, long n, int tab) {
+    for (long i = 0; i < n; i++) { if (tab) smcb::tsincos2pi(u[i], s[i], c[i]); else smcb::fsincos2pi(u[i], s[i], c[i]); }
+}
+void mh_box_muller(const uint32_t *r, double *z, long npairs, int tab) {
+    for (long i = 0; i < npairs; i++) {
+        if (tab) smcb::box_muller_tab(r + 4 * i, z[2 * i], z[2 * i + 1]);
+        else smcb::box_muller_fast(r + 4 * i, z[2 * i], z[2 * i + 1]);
+    }
 }
 // (m, s, q) of v accumulated in batches of 4, as the step kernel does
 void mh_lse3(const double *v, long n, double *out3) {

@@ -38,6 +38,16 @@ def oracle_noise(z, u, scheme, N):
     return orc.InjectedNoise(z, [row[:nu] for row in u])
 
 
+def resync(ref, pf):
+    """After a multinomial tie flip (the device's blocked scan of the exponential spacings rounds differently
+    from NumPy's sequential cumsum, so an ancestor at an exact CDF tie may move by one): carry the device's state
+    into the oracle so that every LATER step is still compared one to one."""
+    ref.X = host(pf.X).copy()
+    ref.wgts = orc.Weights(lw=host(pf.wgts.lw).copy())
+    ref.logLt, ref.log_mean_w = pf.logLt, pf.log_mean_w
+    ref.logLts[-1], ref.ESSs[-1] = pf.logLt, pf.wgts.ESS
+
+
 def models():
     from particles_b200 import kalman, state_space_models as ssm
     return {
@@ -83,12 +93,13 @@ def test_fused_step_by_step_vs_oracle(golden, mname, fkname, scheme, essrmin, N)
     ref = orc.SMC(fk_o, N=N, resampling=scheme, ESSrmin=essrmin, noise=oracle_noise(z, u, scheme, N),
                   keep=True)
     assert pf.fused
-    n_rs = 0
+    n_rs = n_flips = 0
     for t in range(T):
         next(pf)
         ref.step()
         assert pf.t == ref.t == t + 1
         assert pf.rs_flag == ref.rs_flag, f"rs_flag differs at t={t}"
+        keep = slice(None)
         if ref.rs_flag:
             n_rs += 1
             A = host(pf.A)
@@ -97,15 +108,21 @@ def test_fused_step_by_step_vs_oracle(golden, mname, fkname, scheme, essrmin, N)
                 bad = np.flatnonzero(A != ref.A)        # second scan rounding: rare +-1 at CDF ties
                 assert bad.size <= 2 and np.all(np.abs(A[bad] - ref.A[bad]) <= 1)
                 if bad.size:
-                    pytest.skip("ancestor tie moved by scan rounding; trajectories diverge by design")
+                    n_flips += 1
+                    keep = np.setdiff1d(np.arange(N), bad)
             else:
                 assert np.array_equal(A, ref.A), f"ancestors differ at t={t}"
-        np.testing.assert_allclose(host(pf.X), ref.X, rtol=1e-11, atol=1e-13)
-        np.testing.assert_allclose(host(pf.wgts.lw), ref.wgts.lw, rtol=1e-10, atol=1e-10)
-        np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-10)
-        np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-11, atol=1e-10)
-        np.testing.assert_allclose(pf.loglt, ref.loglt, rtol=1e-9, atol=1e-10)
-    assert n_rs > 0
+        np.testing.assert_allclose(host(pf.X)[keep], ref.X[keep], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(host(pf.wgts.lw)[keep], ref.wgts.lw[keep], rtol=1e-10, atol=1e-10)
+        if isinstance(keep, slice):
+            np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-10)
+            np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-11, atol=1e-10)
+            np.testing.assert_allclose(pf.loglt, ref.loglt, rtol=1e-9, atol=1e-10)
+        else:                                           # <= 2 of N particles differ: scalars agree to ~1/N only
+            np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=0.05)
+            np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=0, atol=0.05)
+            resync(ref, pf)
+    assert n_rs > 0 and n_flips <= 3
     np.testing.assert_allclose(host(pf.W), ref.wgts.W, rtol=1e-9, atol=1e-300)
     assert np.array_equal(pf.summaries.rs_flags, ref.rs_flags)
     np.testing.assert_allclose(pf.summaries.ESSs, ref.ESSs, rtol=1e-10)
@@ -301,6 +318,29 @@ def test_full_size_properties_1e7(golden_stats):
     assert 1 <= w.ESS <= N and abs(float(w.W.sum().item()) - 1) < 1e-10
 
 
+def test_north_star_parity_1e7_T1000(golden_stats):
+    """THE north-star statement at its own size: bootstrap filter of StochVol, N = 1e7, T = 1000, systematic,
+    ESSrmin 0.5 (BASELINE config 2).  logLt within 3 sigma of the reference's own NumPy runs and the reference's
+    number of resampling steps.  sigma: the reference's run-to-run sd at N = 1e5 (8 seeded runs, golden_stats)
+    scaled by sqrt(1e5 / 1e7), plus the standard error of the reference mean itself."""
+    import particles_b200 as pb
+    from particles_b200 import state_space_models as ssm
+    N, T = 10_000_000, 1000
+    ref = golden_stats["stat/sv_T1000_N100000/logLt"]
+    nrs = golden_stats["stat/sv_T1000_N100000/n_resample"]
+    mu, sd = ref.mean(), ref.std(ddof=1)
+    sigma = np.sqrt(sd ** 2 * (1e5 / N) + sd ** 2 / len(ref))
+    y = lst(golden_stats["data/sv_seed1_T1000"][:T])
+    for seed in (11, 12):
+        pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y), N=N, seed=seed)
+        pf.run()
+        n_rs = sum(pf.summaries.rs_flags)
+        assert abs(pf.logLt - mu) < 3 * sigma, (pf.logLt, mu, sigma, (pf.logLt - mu) / sigma)
+        assert abs(pf.logLt - mu) / abs(mu) < 5e-5
+        assert nrs.min() - 3 <= n_rs <= nrs.max() + 3, (n_rs, nrs)
+        pf._engine.close()
+
+
 # ------------------------------------------------------------------ d-dimensional models
 def test_plugin_bearings_only_vs_reference(golden_stats):
     """BASELINE config 3 (i): BearingsOnly (IndepProd(Normal, Normal, Dirac, Dirac) state,
@@ -380,6 +420,7 @@ def test_fused_nd_step_by_step_vs_oracle(golden, mname, fkname, scheme):
             next(pf)
             ref.step()
             assert pf.rs_flag == ref.rs_flag, f"rs_flag differs at t={t}"
+            keep = slice(None)
             if ref.rs_flag:
                 n_rs += 1
                 A = host(pf.A)
@@ -387,15 +428,18 @@ def test_fused_nd_step_by_step_vs_oracle(golden, mname, fkname, scheme):
                     bad = np.flatnonzero(A != ref.A)
                     assert bad.size <= 2 and np.all(np.abs(A[bad] - ref.A[bad]) <= 1)
                     if bad.size:
-                        pytest.skip("ancestor tie moved by scan rounding")
+                        keep = np.setdiff1d(np.arange(N), bad)
                 else:
                     assert np.array_equal(A, ref.A), f"ancestors differ at t={t}"
             X = host(pf.X)
             assert X.shape == (N, 4)
-            np.testing.assert_allclose(X, ref.X, rtol=1e-10, atol=1e-12)
-            np.testing.assert_allclose(host(pf.wgts.lw), ref.wgts.lw, rtol=1e-9, atol=1e-9)
-            np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-9)
-            np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-10, atol=1e-9)
+            np.testing.assert_allclose(X[keep], ref.X[keep], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(host(pf.wgts.lw)[keep], ref.wgts.lw[keep], rtol=1e-9, atol=1e-9)
+            if isinstance(keep, slice):
+                np.testing.assert_allclose(pf.wgts.ESS, ref.wgts.ESS, rtol=1e-9)
+                np.testing.assert_allclose(pf.logLt, ref.logLt, rtol=1e-10, atol=1e-9)
+            else:
+                resync(ref, pf)                      # tie moved by scan rounding: carry on from the device state
     assert n_rs > 0
     if mname == "bearings":
         assert np.array_equal(host(pf.X)[:, 2:], ref.X[:, 2:])       # Dirac components: exact sums
@@ -511,9 +555,19 @@ def test_degenerate_weights_follow_numpy_semantics(golden):
     import particles_b200 as pb
     from particles_b200 import kalman, state_space_models as ssm
     y = [np.array([0.1]), np.array([1e200]), np.array([0.2]), np.array([0.0])]
+    N, T = 1000, 4
+    z, u = make_noise(N, T, "systematic", 5)
     lg = kalman.LinearGauss(sigmaX=1.0, sigmaY=1e-3, rho=0.9)
-    pf = pb.SMC(fk=ssm.Bootstrap(ssm=lg, data=y), N=1000, seed=3)
+    pf = pb.SMC(fk=ssm.Bootstrap(ssm=lg, data=y), N=N, noise=(z, u))
     pf.run()
-    assert np.isfinite(pf.summaries.logLts[0]) and pf.summaries.logLts[1] == -np.inf or np.isnan(pf.summaries.logLts[1])
-    assert all(np.isnan(v) or v == -np.inf for v in pf.summaries.logLts[2:])
-    assert pf.summaries.rs_flags[2] is False or pf.summaries.rs_flags[2] is True   # no exception is the point
+    with np.errstate(all="ignore"):
+        ref = orc.SMC(orc.Bootstrap(orc.LinearGauss(sigmaX=1.0, sigmaY=1e-3, rho=0.9), y), N=N,
+                      noise=oracle_noise(z, u, "systematic", N)).run()
+    # SURVEY.md section 9.3 on the fused path: finite first step, then NaN ESS / logLt from the all -inf step on,
+    # `NaN < N/2` is False so nothing resamples -- the very sequence NumPy produces
+    assert np.isfinite(ref.logLts[0]) and np.all(np.isnan(ref.logLts[1:])) and ref.rs_flags[2:] == [False, False]
+    assert pf.summaries.rs_flags == ref.rs_flags
+    np.testing.assert_allclose(pf.summaries.logLts[0], ref.logLts[0], rtol=1e-11)
+    assert np.array_equal(np.isnan(pf.summaries.logLts), np.isnan(ref.logLts))
+    assert np.array_equal(np.isnan(pf.summaries.ESSs), np.isnan(ref.ESSs))
+    np.testing.assert_allclose(pf.summaries.ESSs[0], ref.ESSs[0], rtol=1e-10)

@@ -92,6 +92,17 @@ def test_device_math(pb):
     np.testing.assert_allclose(run(3, v), np.cos(2 * np.pi * v), atol=2e-15, rtol=0)
     exact = [float(mpmath.sin(2 * mpmath.pi * mpmath.mpf(float(t)))) for t in v[:2000]]
     np.testing.assert_allclose(run(2, v)[:2000], exact, rtol=0, atol=1e-15)    # <= 4.5 ulp of 1
+    # the table-assisted family the step kernels run on (fn 4..8; tables staged into shared memory by TMA)
+    e = run(4, x)
+    np.testing.assert_allclose(e[ok], ref[ok], rtol=4.5e-16)
+    assert np.all(e[~ok] == 0.0) and np.isnan(run(4, np.array([np.nan, 1.0]))[0])
+    assert run(4, np.array([710.0, 1.0]))[0] == np.inf
+    np.testing.assert_allclose(run(5, u), np.log(u), rtol=7e-16, atol=3e-19)
+    np.testing.assert_allclose(run(6, v), np.sin(2 * np.pi * v), atol=2e-15, rtol=0)
+    np.testing.assert_allclose(run(7, v), np.cos(2 * np.pi * v), atol=2e-15, rtol=0)
+    np.testing.assert_allclose(run(6, v)[:2000], exact, rtol=0, atol=5e-16)
+    a = np.concatenate([r.uniform(0, 80, 200_000), 2.0 ** r.uniform(-60, 7, 100_000), [1.0, 4.0, 1e-300]])
+    np.testing.assert_allclose(run(8, a), np.sqrt(a), rtol=6e-16)               # rsqrt seed + one third-order step
 
 
 # ----------------------------------------------------------------------- weights

@@ -18,9 +18,9 @@ def ptr(a):
     return None if a is None else a.ctypes.data_as(P)
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2], ids=["polynomial", "table", "small-table"])
+@pytest.fixture(scope="module")
 def mh(request):
-    lib = build_math_host(request.param)
+    lib = build_math_host()
     lib.mh_model_step.restype = C.c_int
     return lib
 
