@@ -160,18 +160,43 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, pf.logLt
 
 
-def cpu_baseline(n, steps, workers=1):
-    """particle-steps/s of the NumPy port; `workers` independent filters in processes
-    (the reference's only parallelism is replica-level: utils.multiplexer / multiSMC)."""
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")        # the live reference's package (oracle/make_ref.sh), if present
+
+
+def have_live_reference():
+    return os.path.isdir(os.path.join(REF_DIR, "particles"))
+
+
+def _ref_worker(args):
+    """The UNMODIFIED reference: particles.SMC on the same workload (oracle/_ref, copied by oracle/make_ref.sh)."""
+    n, steps, seed = args
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import particles
+    from particles import resampling as rrs
+    from particles import state_space_models as rssm
+    y = [np.atleast_1d(v) for v in load_data(steps + 1)]
+    np.random.seed(seed)
+    rrs.systematic(np.full(16, 1.0 / 16))         # numba JIT of inverse_cdf outside the timed region
+    pf = particles.SMC(fk=rssm.Bootstrap(ssm=rssm.StochVol(), data=y), N=n, resampling=SCHEME, ESSrmin=ESSRMIN)
+    next(pf)                                       # warm-up step (page faults, allocator)
     t0 = time.perf_counter()
+    for _ in range(steps):
+        next(pf)
+    return time.perf_counter() - t0, pf.logLt
+
+
+def cpu_baseline(n, steps, workers=1, live=False):
+    """particle-steps/s of the live reference (`live`) or of the NumPy port; `workers` independent filters in
+    processes (the reference's only parallelism is replica-level: utils.multiplexer / multiSMC)."""
+    fn = _ref_worker if live else _cpu_worker
     if workers == 1:
-        dt, _ = _cpu_worker((n, steps, 1))
+        dt, _ = fn((n, steps, 1))
         wall = dt
     else:
         import multiprocessing as mp
         with mp.get_context("spawn").Pool(workers) as pool:
-            t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(n, steps, 1 + i) for i in range(workers)])
+            res = pool.map(fn, [(n, steps, 1 + i) for i in range(workers)])
             wall = max(r[0] for r in res)
     return workers * n * steps / wall, wall
 
@@ -192,9 +217,15 @@ def run_reference(args):
     n = N_PER_GPU
     K = max(1, min(args.steps, 4))              # bounded sample: ~3 s per step per worker
     reps = max(1, min(args.warmup, 1))
+    live = have_live_reference()
     for _ in range(reps):
-        cpu_baseline(n // 10, 1, 1)
-    value, wall = cpu_baseline(n, K, workers)
+        cpu_baseline(n // 10, 1, 1, live)
+    value, wall = cpu_baseline(n, K, workers, live)
+    port_value = cpu_baseline(n, K, workers, False)[0] if live else value
+    kind = "reference" if live else "port"
+    what = ("the reference's own particles.SMC (oracle/_ref, copied from the reference checkout by "
+            "oracle/make_ref.sh)" if live else
+            "oracle NumPy restatement of particles.core.SMC (no oracle/_ref on this box)")
     out = {
         "impl": "reference", "metric": "particle-steps/sec (N x T), Bootstrap SV", "value": value,
         "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": reps,
@@ -202,10 +233,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"StochVol bootstrap N={n} systematic ESSrmin=0.5 (config 2), "
                                f"{workers} replica filters in {workers} processes"},
-        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": workers, "kind": "port",
-                         "sample": f"{K} filter steps at N={n} per worker after 1 warm-up step; "
-                                   "oracle NumPy restatement of particles.core.SMC (the reference is "
-                                   "pure Python and cannot travel to this box)"},
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": workers, "kind": kind,
+                         "sample": f"{K} filter steps at N={n} per worker after 1 warm-up step; " + what,
+                         "port_value": port_value},
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -215,6 +245,44 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
+def multi_gpu_parity(table, spec, y, rank, world):
+    """Driver-side evidence that the sharded filter is correct (every rank calls this):
+    (1) all ranks hold bit-identical summaries of the timed run;
+    (2) the EXACT global-resampling mode on `world` GPUs reproduces the single-device filter of the same seed and
+        the same total N (Philox counters follow the global particle index): max |delta logLt| over all steps."""
+    import torch
+    import torch.distributed as dist
+    from particles_b200.core import _FusedEngine
+    from particles_b200.parallel import ShardedFilter
+    t = torch.from_numpy(np.ascontiguousarray(table)).cuda()
+    allt = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    identical = all(bool(torch.equal(o, t)) for o in allt)
+    n_x, T_x = 200_000, 200
+    sp = dict(spec)
+    sp["data"] = y[:T_x].reshape(-1, 1).copy()
+    f = ShardedFilter(sp, n_x, SCHEME, 0.5, 4242, rank, world, resampling_mode="global")
+    f.step(T_x)
+    f.state()
+    tab = f.summ[:T_x].clone()
+    f.close()
+    res = torch.zeros(3, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        e = _FusedEngine(sp, n_x * world, SCHEME, 0.5, 4242)
+        e.step(T_x)
+        one = e.summ[:T_x].clone()
+        e.close()
+        res[0] = (one[:, 1] - tab[:, 1]).abs().max()
+        res[1] = float(torch.equal(one[:, 2], tab[:, 2]))
+        res[2] = tab[:, 2].sum()
+    dist.broadcast(res, 0)
+    return {"rank_identical_summaries": identical,
+            "global_vs_single_device": {"max_abs_dlogLt": float(res[0]), "same_resampling_decisions": bool(res[1] > 0),
+                                        "resampling_steps": int(res[2]), "n_per_gpu": n_x, "T": T_x,
+                                        "ok": bool(res[0] < 1e-9 and res[1] > 0)}}
+
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -366,16 +434,22 @@ def run_b200(args):
                "d2h_bytes_per_step": 32, "seconds": dt, "seconds_all_runs": runs, "logLt": ll,
                "api": "particles_b200.parallel.ShardedSMC(fk=Bootstrap(StochVol(), data), N).run() on every rank; "
                       "median of 3 whole calls, max over ranks"}
+    multi = None
+    if world > 1:
+        multi = multi_gpu_parity(table, spec, y, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, wall = cpu_baseline(n, 4, 1)
-        cpu = {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-               "sample": f"4 filter steps at N={n} after 1 warm-up step, single process "
-                         "(the reference runs one filter on one core); oracle NumPy restatement"}
+        live = have_live_reference()
+        v, wall = cpu_baseline(n, 4, 1, live)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "reference" if live else "port",
+               "sample": f"4 filter steps at N={n} after 1 warm-up step, single process (the reference runs one "
+                         "filter on one core); " + ("the reference's own particles.SMC from oracle/_ref" if live
+                                                    else "oracle NumPy restatement"),
+               "port_value": cpu_baseline(n, 4, 1, False)[0] if live else v}
     total_n = n * world
     out = {
         "metric": "particle-steps/sec (N x T), Bootstrap SV", "value": total_n * K / (ms * 1e-3),
@@ -396,6 +470,8 @@ def run_b200(args):
                                "island resampling: a different (consistent) estimator from the reference's global "
                                "scheme; logLt parity is statistical"),
     }
+    if multi is not None:
+        out["parity"]["multi_gpu"] = multi
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -113,6 +113,20 @@ static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) 
         a.chunk = chunk;
         f->grid_move = (int)g;
         a.grid = f->grid_move;
+        // slabs of the streaming branch (smcb_step.cuh): records in the (otherwise idle) CDF staging buffers
+        const bool apf = d->fk == SMCB_FK_APF || d->fk == SMCB_FK_AUXBOOT;
+        const bool mom = d->moments != nullptr || d->world > 1;
+        a.slab_lane = (!apf && !mom) ? 1 : 0;
+        a.slab_stride = a.slab_lane ? 96 : 4 + (apf ? 4 : 0) + (mom ? 2 * d->dim : 0);
+        const int64_t cap = f->slab_doubles / a.slab_stride;
+        const int64_t n_iter = (chunk + 32 * SMCB_KU - 1) / (32 * SMCB_KU);
+        int64_t n_small = n_iter / 8;
+        if (n_small > cap / 4) n_small = cap / 4;
+        int64_t slab_it = (n_iter - n_small + (cap - n_small) - 1) / (cap - n_small);
+        if (slab_it < 2) slab_it = 2;
+        if (const char *e = getenv("SMCB_SLAB_IT")) { int v = atoi(e); if (v >= slab_it) slab_it = v; }   // experiments
+        a.slab_it = (int)slab_it;
+        a.slab_small = (int)n_small;
     }
     a.world = d->world > 1 ? d->world : 1;
     a.rank = d->world > 1 ? d->rank : 0;

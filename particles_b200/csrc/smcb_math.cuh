@@ -203,6 +203,26 @@ __device__ __forceinline__ double texp_core(double x) {
     const double v = fma(tj, em1, tj);                     // in [1, 2)
     return __hiloint2double(__double2hiint(v) + ((k >> kExpTabBits) << 20), __double2loint(v));
 }
+// same with the power of two clamped to the normal range (two integer min / max instead of two fp64 selects):
+// the result SATURATES at ~2^-1022 / ~2^1024 instead of reaching 0 / +inf; +-inf and NaN give NaN.  For arguments
+// that are finite by construction (a model's exp of a finite state, a finite log-weight minus its maximum).
+__device__ __forceinline__ double texp_sat(double x) {
+    const double t = fma(x, kExpScaleT, kRintMagic);
+    const double kd = t - kRintMagic;
+    const int k = __double2loint(t);
+    double r = fma(kd, -kLn2HiT, x);
+    r = fma(kd, -kLn2LoT, r);
+    const double tj = mtab()[kTabExp + (k & (kExpTabN - 1))];
+    const double h = fma(r, kImmSixth, 0.5);
+    const double em1 = fma(r * r, h, r);
+    const double v = fma(tj, em1, tj);
+    // K >> 12 from BOTH words of the magic sum (its mantissa is 2^51 + K): right for |x| up to ~1e9
+    int q = (int)__funnelshift_r((unsigned int)k, (unsigned int)__double2hiint(t), kExpTabBits);
+    q = q < -1022 ? -1022 : q;
+    q = q > 1023 ? 1023 : q;
+    return __hiloint2double(__double2hiint(v) + (q << 20), __double2loint(v));
+}
+
 // x <= ~709; 0 for x < -708 (incl. -inf), +inf for x > 709, NaN for NaN
 __device__ __forceinline__ double texp(double x) {
     double res = texp_core(x);
@@ -276,8 +296,12 @@ __device__ __forceinline__ void normal_pair_tab(const Philox &key, uint64_t pair
     box_muller_tab(r, z0, z1);
 }
 
-// the models' exp (smcb_models.cuh): the table family -- models only run inside the step kernels
-__device__ __forceinline__ double mexp(double x) { return texp(x); }
+// the models' exp (smcb_models.cuh): the table family -- models only run inside the step kernels.  Saturating:
+// exp(-x) of a log-volatility beyond +-708 clamps at 2^+-1023, which the weight algebra treats like inf / 0.
+__device__ __forceinline__ double mexp(double x) { return texp_sat(x); }
+
+// true iff v is +-inf or NaN (integer test on the exponent field: no fp64 pipe)
+__device__ __forceinline__ bool nonfinite(double v) { return (__double2hiint(v) & 0x7FF00000) == 0x7FF00000; }
 
 // ---------------------------------------------------------------------------
 // (max, sum exp, sum exp^2) accumulation of a small batch with ONE exp per value:

@@ -45,8 +45,10 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 // each other (progress throttle in the streaming loop).
 template <class M> struct StepCfg {
     static constexpr int BS = (M::D == 1) ? 768 : 512;
-    static constexpr int kStage = 4 * BS;             // doubles of CDF staged per output tile (2 BS outputs)
-    // dynamic shared memory: the math tables (smcb_tables.h, 64 KB), then two CDF slices
+    static constexpr int kStage = 8 * BS;             // doubles of CDF staged per output tile (2 BS outputs)
+    // dynamic shared memory: the math tables (smcb_tables.h, 64 KB), then two CDF slices (resampling branch) which
+    // the streaming branch reuses for its slab records
+    static constexpr int kSlabDoubles = 2 * kStage;
     static constexpr size_t dyn_smem = kMathTabBytes + 2 * kStage * sizeof(double);
 };
 
@@ -78,6 +80,10 @@ struct FilterArgs {
     unsigned long long *bar; // grid-barrier arrivals, never reset
     double *blk_agg;         // multinomial: per-CTA sums of the exponential spacings (grid + 1)
     const double *math_tab;  // smcb_tables.h, built at context creation
+    int slab_it;             // iterations per slab of the streaming branch (host: chosen so the records fit)
+    int slab_small;          // trailing iterations of a CTA's range handed out as single-iteration slabs
+    int slab_lane;           // 1: a slab record holds the 32 lanes' own (m, s, q) (96 doubles); 0: their warp reduction
+    int slab_stride;         // doubles per slab record: 4 (+ 4 auxiliary) (+ 2 D moments)
     int64_t n, n_global, index_offset, T;
     int dy;
     int world, rank;
@@ -141,17 +147,24 @@ __device__ __forceinline__ double shift_factor(double m, double M) {
 }
 
 // ---------------------------------------------------------------------------
-// block-wide fixed-order reductions; every thread receives the result
+// block-wide fixed-order reductions; every thread receives the result.  Two levels: butterfly inside each warp,
+// then warp 0 reduces the per-warp values (lane = warp index) and parks the totals in shared memory -- never
+// "every thread walks all warps' values" (with 24 warps that was 7 us of shared-memory traffic per call).
+// smem: (BS/32 + 1) x NV doubles.
 // ---------------------------------------------------------------------------
-template <int NV, int BS>
-__device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (BS/32) x NV */) {
+__device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }   // NaN wins
+
+template <int NV, int BS, bool MAX>
+__device__ __forceinline__ void block_reduce_all(double (&v)[NV], double *smem) {
+    constexpr int NWARP = BS / 32;
+    static_assert(NWARP <= 32, "one lane per warp in the second level");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NV; j++) {
 #pragma unroll
         for (int mask = 16; mask > 0; mask >>= 1) {
             const double o = __shfl_xor_sync(0xffffffffu, v[j], mask);
-            v[j] = (o > v[j] || o != o) ? o : v[j];          // NaN wins (np.max of a NaN array is NaN)
+            v[j] = MAX ? nanmax(v[j], o) : v[j] + o;
         }
     }
     if (lane == 0) {
@@ -159,41 +172,27 @@ __device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem /* (
         for (int j = 0; j < NV; j++) smem[warp * NV + j] = v[j];
     }
     __syncthreads();
+    if (warp == 0) {
 #pragma unroll
-    for (int j = 0; j < NV; j++) {
-        double m = smem[j];
+        for (int j = 0; j < NV; j++) {
+            double x = (lane < NWARP) ? smem[lane * NV + j] : (MAX ? -CUDART_INF : 0.0);
 #pragma unroll
-        for (int w = 1; w < BS / 32; w++) {
-            const double o = smem[w * NV + j];
-            m = (o > m || o != o) ? o : m;
+            for (int mask = 16; mask > 0; mask >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, x, mask);
+                x = MAX ? nanmax(x, o) : x + o;
+            }
+            if (lane == 0) smem[NWARP * NV + j] = x;
         }
-        v[j] = m;
     }
     __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = smem[NWARP * NV + j];
+    __syncthreads();
 }
-
 template <int NV, int BS>
-__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem /* (BS/32) x NV */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < NV; j++) {
-#pragma unroll
-        for (int mask = 16; mask > 0; mask >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], mask);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < NV; j++) smem[warp * NV + j] = v[j];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NV; j++) {
-        double s = smem[j];
-#pragma unroll
-        for (int w = 1; w < BS / 32; w++) s += smem[w * NV + j];
-        v[j] = s;
-    }
-    __syncthreads();
-}
+__device__ __forceinline__ void block_max_all(double (&v)[NV], double *smem) { block_reduce_all<NV, BS, true>(v, smem); }
+template <int NV, int BS>
+__device__ __forceinline__ void block_sum_all(double (&v)[NV], double *smem) { block_reduce_all<NV, BS, false>(v, smem); }
 
 // ---------------------------------------------------------------------------
 // per-thread accumulators: (max, sum exp, sum exp^2) of the log-weights with ONE exp per value (the
@@ -214,28 +213,31 @@ __device__ __forceinline__ void acc_init(Acc<D> &a) {
     for (int c = 0; c < D; c++) { a.sx[c] = 0.0; a.sxx[c] = 0.0; }
 }
 
-template <int NV, int D>
-__device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], const double (&x)[NV][D], bool mom) {
+// FINITE: the caller has checked that no value is +-inf / NaN (integer test, nonfinite()): the exponentials then
+// need no range select (texp_sat), the maxima no NaN handling, and no slot is masked.  MOM is a template
+// parameter so that the moment arithmetic is absent (not predicated off) when nobody collects moments.
+template <int NV, int D, bool FINITE, bool MOM>
+__device__ __forceinline__ void acc_add_batch_t(Acc<D> &a, const double (&v)[NV], const double (&x)[NV][D]) {
     double mb = v[0];
 #pragma unroll
-    for (int j = 1; j < NV; j++) mb = fmax(mb, v[j]);
-    if (mb > a.w.m) {                       // also the first time (m = -inf): fexp(-inf) = 0
+    for (int j = 1; j < NV; j++) mb = FINITE ? (v[j] > mb ? v[j] : mb) : fmax(mb, v[j]);
+    if (mb > a.w.m) {                       // also the first time (m = -inf): exp(-inf) = 0
         const double r = texp_neg(a.w.m - mb);
         a.w.s *= r;
         a.w.q *= r * r;
-        if (mom) {
+        if (MOM) {
 #pragma unroll
             for (int c = 0; c < D; c++) { a.sx[c] *= r; a.sxx[c] *= r; }
         }
         a.w.m = mb;
     }
-    if (a.w.m == -CUDART_INF) return;       // nothing but -inf so far
+    if (!FINITE && a.w.m == -CUDART_INF) return;       // nothing but -inf so far
 #pragma unroll
     for (int j = 0; j < NV; j++) {
-        const double e = texp_neg(v[j] - a.w.m);
+        const double e = FINITE ? texp_sat(v[j] - a.w.m) : texp_neg(v[j] - a.w.m);
         a.w.s += e;
         a.w.q = fma(e, e, a.w.q);
-        if (mom && v[j] != -CUDART_INF) {
+        if (MOM && (FINITE || v[j] != -CUDART_INF)) {
 #pragma unroll
             for (int c = 0; c < D; c++) {
                 const double ex = e * x[j][c];
@@ -245,19 +247,112 @@ __device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], 
         }
     }
 }
+template <int NV, int D, bool FINITE = false>
+__device__ __forceinline__ void acc_add_batch(Acc<D> &a, const double (&v)[NV], const double (&x)[NV][D], bool mom) {
+    if (mom) acc_add_batch_t<NV, D, FINITE, true>(a, v, x);
+    else acc_add_batch_t<NV, D, FINITE, false>(a, v, x);
+}
 
 struct StepSmem {
     double red[32 * 16];
     int prog[32];
+    int next;                 // next slab / iteration of the streaming branch
+    int pad;
     double peer[8][kMailStride];
     double goff[9], gpi[8];
     double pref[2];
 };
 
+// exp(m - M) with the table family (inside the step kernels)
+__device__ __forceinline__ double shift_factor_t(double m, double M) {
+    return (m == -CUDART_INF) ? 0.0 : texp_neg(m - M);
+}
+
+__device__ __forceinline__ double warp_max_nan(double v) {
+#pragma unroll
+    for (int mask = 16; mask > 0; mask >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, v, mask);
+        v = (o > v || o != o) ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int mask = 16; mask > 0; mask >>= 1) v += __shfl_xor_sync(0xffffffffu, v, mask);
+    return v;
+}
+
+// one slab of the streaming branch: the warp's thread accumulators -> one record in shared memory
+// [m, s, q, -][aux m, s, q, -][sx[D], sxx[D]]; fixed butterfly order, so the record depends on the slab alone
+template <int D, bool APF>
+__device__ __forceinline__ void warp_reduce_to_slab(const Acc<D> &sa, const Lse3 &sx, bool mom, double *rec, int lane) {
+    const double M = warp_max_nan(sa.w.m);
+    const double e = shift_factor_t(sa.w.m, M);
+    const double s = warp_sum(sa.w.s * e), q = warp_sum(sa.w.q * (e * e));
+    if (lane == 0) { rec[0] = M; rec[1] = s; rec[2] = q; }
+    int off = 4;
+    if (APF) {
+        const double Ma = warp_max_nan(sx.m);
+        const double ea = shift_factor_t(sx.m, Ma);
+        const double as_ = warp_sum(sx.s * ea), aq = warp_sum(sx.q * (ea * ea));
+        if (lane == 0) { rec[4] = Ma; rec[5] = as_; rec[6] = aq; }
+        off = 8;
+    }
+    if (mom) {
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            const double a1 = warp_sum(sa.sx[c] * e), a2 = warp_sum(sa.sxx[c] * e);
+            if (lane == 0) { rec[off + c] = a1; rec[off + D + c] = a2; }
+        }
+    }
+}
+
+// fold one slab record into a thread accumulator (fixed order: the caller walks the slabs in slab order)
+template <int D, bool APF>
+__device__ __forceinline__ void acc_merge_slab(Acc<D> &acc, Lse3 &aux, bool mom, const double *rec) {
+    {
+        const double bm = rec[0];
+        const double M = (bm > acc.w.m || bm != bm) ? bm : acc.w.m;
+        const double ea = shift_factor_t(acc.w.m, M), eb = shift_factor_t(bm, M);
+        acc.w.s = acc.w.s * ea + rec[1] * eb;
+        acc.w.q = acc.w.q * (ea * ea) + rec[2] * (eb * eb);
+        acc.w.m = M;
+        if (mom) {
+            const int off = APF ? 8 : 4;
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+                acc.sx[c] = acc.sx[c] * ea + rec[off + c] * eb;
+                acc.sxx[c] = acc.sxx[c] * ea + rec[off + D + c] * eb;
+            }
+        }
+    }
+    if (APF) {
+        const double bm = rec[4];
+        const double M = (bm > aux.m || bm != bm) ? bm : aux.m;
+        const double ea = shift_factor_t(aux.m, M), eb = shift_factor_t(bm, M);
+        aux.s = aux.s * ea + rec[5] * eb;
+        aux.q = aux.q * (ea * ea) + rec[6] * (eb * eb);
+        aux.m = M;
+    }
+}
+
 // this CTA's row of the partials of step t: block reduction of the thread accumulators
 template <int D, bool APF, int BS>
-__device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, const Acc<D> &acc, const Lse3 &aux,
-                                              bool mom, StepSmem &sh) {
+__device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, Acc<D> acc, Lse3 aux,
+                                              bool mom, StepSmem &sh, const double *s_slab = nullptr, int n_slab = 0) {
+    if (n_slab > 0) {                       // streaming branch: the slab records, in a fixed order per thread
+        __syncthreads();
+        if (a.slab_lane) {                  // one (m, s, q) per lane and slab: record r = slab * 32 + lane
+            for (int r = threadIdx.x; r < n_slab * 32; r += BS) {
+                const double *rec = s_slab + (size_t)(r >> 5) * a.slab_stride + (r & 31);
+                const double rr[3] = {rec[0], rec[32], rec[64]};
+                acc_merge_slab<D, false>(acc, aux, false, rr);
+            }
+        } else {
+            for (int sl = threadIdx.x; sl < n_slab; sl += BS)
+                acc_merge_slab<D, APF>(acc, aux, mom, s_slab + (size_t)sl * a.slab_stride);
+        }
+    }
     double mx[2] = {acc.w.m, APF ? aux.m : -CUDART_INF};
     block_max_all<2, BS>(mx, sh.red);
     const double ew = shift_factor(acc.w.m, mx[0]);
@@ -730,12 +825,15 @@ __device__ __forceinline__ int shard_of(const double *goff, const double *gpi, i
 #define SMCB_KU 2
 #endif
 #ifndef SMCB_THROTTLE
-#define SMCB_THROTTLE 1          // iterations a warp may run ahead of the slowest warp of its CTA (0: off)
+#define SMCB_THROTTLE 1          // SMCB_SCHED 0: iterations a warp may run ahead of the slowest warp of its CTA (0: off)
+#endif
+#ifndef SMCB_SCHED
+#define SMCB_SCHED 2             // 0 static + throttle, 1 dynamic (experiment, order-dependent sums), 2 dynamic slabs
 #endif
 #ifdef SMCB_TRACE
-// per-CTA timeline of the LAST launch of the step kernel: {start, prologue done, main loop done, smid} in ns,
-// then per warp the time its main loop ended
-__device__ unsigned long long g_trace[4 * 256 + 32 * 256];
+// per-CTA timeline of the LAST launch of the step kernel: {start, dependency resolved, prologue done, main loop
+// done, exit, smid} in ns (8 words per CTA), then per warp the time its main loop ended
+__device__ unsigned long long g_trace[8 * 256 + 32 * 256];
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -746,8 +844,8 @@ __device__ __forceinline__ unsigned int smid() {
     asm volatile("mov.u32 %0, %smid;" : "=r"(r));
     return r;
 }
-#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[4 * blockIdx.x + (slot)] = gtimer(); } while (0)
-#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[4 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
+#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[8 * blockIdx.x + (slot)] = gtimer(); } while (0)
+#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
 #else
 #define SMCB_TRACE_MARK(slot) do { } while (0)
 #define SMCB_TRACE_WARP() do { } while (0)
@@ -767,17 +865,18 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     __shared__ long long s_hi;
     __shared__ double s_warp[BS / 32];
 #ifdef SMCB_TRACE
-    if (threadIdx.x == 0) { g_trace[4 * blockIdx.x] = gtimer(); g_trace[4 * blockIdx.x + 3] = smid(); }
+    if (threadIdx.x == 0) { g_trace[8 * blockIdx.x] = gtimer(); g_trace[8 * blockIdx.x + 5] = smid(); }
 #endif
     // the tables are constants: their copy may start before the previous kernel has retired
-    if (threadIdx.x == 0) mtab_issue(a.math_tab, &s_tabbar);
+    if (threadIdx.x == 0) { mtab_issue(a.math_tab, &s_tabbar); sh.next = 0; }
     // everything below reads what the previous kernel of the stream wrote (programmatic dependent launch:
     // this kernel may have been scheduled before its predecessor retired)
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
+    SMCB_TRACE_MARK(1);
     const StepDecision dec = step_prologue<APF, BS>(a, t, sh, blockIdx.x == 0, true);
     mbar_wait(&s_tabbar, 0);                           // (the prologue's barriers made the init visible)
-    SMCB_TRACE_MARK(1);
+    SMCB_TRACE_MARK(2);
     const int cur = (int)((t - 1) & 1);                // step s writes buffers [s & 1]
     const bool rs = dec.rs != 0;
     const double reset_c = dec.reset_c;
@@ -798,6 +897,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     Acc<D> acc;
     acc_init(acc);
     Lse3 aux = lse3_empty();
+    int n_slab = 0;                                    // slab records of the streaming branch (SMCB_SCHED 2)
 
     // propagate + reweight one pair of particles; writes x', lw'; returns x', lw' (and the auxiliary
     // log-weights of the next step for an APF), -inf in masked slots
@@ -841,21 +941,88 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     };
 
     if (!rs) {
-        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass, kU pairs in flight per thread.  The warps
-        // of the CTA pace each other: none starts iteration i + SMCB_THROTTLE + 1 before all have finished i.
+        // A = arange(N), Xp = X (core.py:335-336): pure streaming pass.  Work unit = one "iteration" of a warp:
+        // kU x 32 consecutive pairs (kU coalesced 512-byte rows per array), kU pairs in flight per thread.
         constexpr int kU = SMCB_KU;
-        constexpr int64_t stride = BS;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#if SMCB_THROTTLE
-        if (threadIdx.x < 32) sh.prog[threadIdx.x] = (threadIdx.x < BS / 32) ? 0 : INT_MAX;
-        __syncthreads();
-        int it = 0;
-#endif
-        for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kU * stride) {
-            double xp[kU][2][D], base[kU][2], l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
+        constexpr int kIt = 32 * kU;                                          // pairs per iteration
+        const int lane = threadIdx.x & 31;
+        const int npl = (int)(pend - pstart);                                 // pairs of this CTA (< 2^31)
+        const int n_iter = (npl + kIt - 1) / kIt;
+        // iterations made of complete pairs only run without any bounds test (the odd last particle and the ragged
+        // end of the range take the general path)
+        const int64_t whole = (n >> 1) < pend ? (n >> 1) : pend;
+        const int n_full = whole > pstart ? (int)((whole - pstart) / kIt) : 0;
+        const bool fast_ok = (zin == nullptr) && vec_x;
+        const double *__restrict__ lwi_c = lwi + 2 * pstart;
+        const double *__restrict__ Xi_c = Xi + 2 * pstart;
+        double *__restrict__ lwo_c = lwo + 2 * pstart;
+        double *__restrict__ Xo_c = Xo + 2 * pstart;
+        const uint64_t gpair0 = (uint64_t)((a.index_offset >> 1) + pstart);
+        // one iteration: pairs (relative to pstart) i * kIt + u * 32 + lane
+        auto iteration = [&](int i, Acc<D> &ac, Lse3 &ax) {
+            double l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
+            if (fast_ok && i < n_full) {
+                double xp[kU][2][D], base[kU][2];
 #pragma unroll
-            for (int u = 0; u < kU; u++) {                        // all loads first (MLP)
-                const int64_t p = p0 + u * stride;
+                for (int u = 0; u < kU; u++) {                    // all loads first (MLP)
+                    const int o2 = 2 * (i * kIt + u * 32 + lane);
+                    const double2 tl = ld2(lwi_c + o2);
+                    base[u][0] = tl.x; base[u][1] = tl.y;
+#pragma unroll
+                    for (int c = 0; c < D; c++) {
+                        const double2 tx = ld2(Xi_c + (size_t)c * n + o2);
+                        xp[u][0][c] = tx.x; xp[u][1][c] = tx.y;
+                    }
+                }
+                bool odd = false;                                 // some value is +-inf / NaN (integer test)
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const int prel = i * kIt + u * 32 + lane;
+                    double z[2][NZ];
+#pragma unroll
+                    for (int c = 0; c < NZ; c++)
+                        normal_pair_tab(a.key, gpair0 + (uint64_t)prel, (uint32_t)t, (uint32_t)c, z[0][c], z[1][c]);
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; j2++) {
+                        double d;
+                        model_move<M, FK>(model, k, xp[u][j2], z[j2], x[2 * u + j2], d);
+                        l[2 * u + j2] = base[u][j2] + d;                      // Weights.add, resampling.py:241-244
+                        odd |= nonfinite(l[2 * u + j2]);
+                        if (APF) {
+                            av[APF ? 2 * u + j2 : 0] = last_apf ? l[2 * u + j2] + model_logeta<M>(model, k, x[2 * u + j2])
+                                                                : -CUDART_INF;
+                            odd |= nonfinite(av[APF ? 2 * u + j2 : 0]);
+                        }
+                    }
+                }
+                if (odd) {                                        // rare: NaN -> -inf (resampling.py:220)
+#pragma unroll
+                    for (int q = 0; q < 2 * kU; q++) {
+                        l[q] = fix_nan(l[q]);
+                        if (APF) av[APF ? q : 0] = fix_nan(av[APF ? q : 0]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const int o2 = 2 * (i * kIt + u * 32 + lane);
+#pragma unroll
+                    for (int c = 0; c < D; c++) st2(Xo_c + (size_t)c * n + o2, x[2 * u][c], x[2 * u + 1][c]);
+                    st2(lwo_c + o2, l[2 * u], l[2 * u + 1]);
+                }
+                if (!odd) {
+                    acc_add_batch<2 * kU, D, true>(ac, l, x, mom);
+                } else {
+                    acc_add_batch<2 * kU, D, false>(ac, l, x, mom);
+                }
+                if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(ax, av);
+                return;
+            }
+            // general path: ragged end of the range, the odd last particle, injected normals, odd SoA stride
+            double xp[kU][2][D], base[kU][2];
+            const int64_t qbase = pstart + (int64_t)i * kIt;
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int64_t p = qbase + u * 32 + lane;
                 if (p < pend && 2 * p + 1 < n) {
                     double2 tl = ld2(lwi + 2 * p);
                     base[u][0] = tl.x; base[u][1] = tl.y;
@@ -876,7 +1043,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
-                const int64_t p = p0 + u * stride;
+                const int64_t p = qbase + u * 32 + lane;
                 if (p < pend) {
                     do_pair(p, xp[u], base[u], reinterpret_cast<double (&)[2][D]>(x[2 * u]), l + 2 * u,
                             APF ? av + 2 * u : av);
@@ -887,20 +1054,71 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
                     for (int c = 0; c < D; c++) { x[2 * u][c] = 0.0; x[2 * u + 1][c] = 0.0; }
                 }
             }
-            acc_add_batch<2 * kU, D>(acc, l, x, mom);
-            if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(aux, av);
-#if SMCB_THROTTLE
+            acc_add_batch<2 * kU, D>(ac, l, x, mom);
+            if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(ax, av);
+        };
+#if SMCB_SCHED == 0
+        constexpr int NW = BS / 32;
+        const int warp = threadIdx.x >> 5;
+        // static round-robin of the iterations over the warps; the warps pace each other (none starts its
+        // (k + SMCB_THROTTLE + 1)-th iteration before all have finished their k-th)
+        if (threadIdx.x < 32) sh.prog[threadIdx.x] = (threadIdx.x < NW) ? 0 : INT_MAX;
+        __syncthreads();
+        int it = 0;
+        for (int i = warp; i < n_iter; i += NW) {
+            iteration(i, acc, aux);
             it++;
+#if SMCB_THROTTLE
             if (lane == 0) *reinterpret_cast<volatile int *>(&sh.prog[warp]) = it;
-            for (;;) {
+            for (int spin = 0; spin < (1 << 16); spin++) {          // bounded: pacing is an optimisation only
                 const int mn = __reduce_min_sync(0xffffffffu, *reinterpret_cast<volatile int *>(&sh.prog[lane]));
                 if (mn >= it - SMCB_THROTTLE) break;
                 __nanosleep(100);
             }
 #endif
         }
-#if SMCB_THROTTLE
         if (lane == 0) *reinterpret_cast<volatile int *>(&sh.prog[warp]) = INT_MAX;    // done: nobody waits for this warp
+#elif SMCB_SCHED == 1
+        // EXPERIMENT: dynamic iterations, thread accumulators (summation order depends on the schedule)
+        for (;;) {
+            int i = 0;
+            if (lane == 0) i = atomicAdd(&sh.next, 1);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n_iter) break;
+            iteration(i, acc, aux);
+        }
+#else
+        // dynamic slabs: a warp takes the next slab of `slab_it` consecutive iterations from a shared counter, so
+        // the warps of the SM drift apart (one warp's loads overlap the others' arithmetic) and all retire within
+        // one slab of each other whatever the scheduler's priorities.  Determinism: a slab's statistics are parked in
+        // shared memory as one record per slab -- the 32 lanes' own (max, sum exp, sum exp^2), or, when auxiliary
+        // weights / moments make that too large, their fixed-order reduction over the warp -- and write_partial
+        // merges the records in slab order, so the result does not depend on which warp ran which slab.  The tail of
+        // the range is cut into single-iteration slabs (short drain).  The records alias the CDF staging buffers,
+        // which only the resampling branch uses.
+        const int slab_it = a.slab_it;
+        const int n_small = a.slab_small < n_iter ? a.slab_small : n_iter;
+        const int it_small0 = n_iter - n_small;                               // first single-iteration slab
+        const int n_big = (it_small0 + slab_it - 1) / slab_it;                // slabs of (up to) slab_it iterations
+        n_slab = n_big + n_small;
+        double *s_slab = s_stage;
+        const bool lane_rec = a.slab_lane != 0;
+        for (;;) {
+            int sl = 0;
+            if (lane == 0) sl = atomicAdd(&sh.next, 1);
+            sl = __shfl_sync(0xffffffffu, sl, 0);
+            if (sl >= n_slab) break;
+            const int i0 = sl < n_big ? sl * slab_it : it_small0 + (sl - n_big);
+            const int rem = it_small0 - i0;
+            const int cnt = sl < n_big ? (rem < slab_it ? rem : slab_it) : 1;
+            Acc<D> sa;
+            acc_init(sa);
+            Lse3 sx = lse3_empty();
+            for (int k_ = 0; k_ < cnt; k_++) iteration(i0 + k_, sa, sx);
+            double *rec = s_slab + (size_t)sl * a.slab_stride;
+            if (lane_rec) { rec[lane] = sa.w.m; rec[32 + lane] = sa.w.s; rec[64 + lane] = sa.w.q; }
+            else warp_reduce_to_slab<D, APF>(sa, sx, mom, rec, lane);
+        }
 #endif
         SMCB_TRACE_WARP();
     } else {
@@ -1170,8 +1388,9 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             }
         }
     }
-    SMCB_TRACE_MARK(2);
-    write_partial<D, APF, BS>(a, t, acc, aux, mom, sh);
+    SMCB_TRACE_MARK(3);
+    write_partial<D, APF, BS>(a, t, acc, aux, mom, sh, s_stage, n_slab);
+    SMCB_TRACE_MARK(4);
 }
 
 // the prologue alone (one CTA): finalises the last enqueued step so that the host can read its summaries
@@ -1204,7 +1423,8 @@ struct smcb_filter {
     char *mem;            // header (StepState[2], barrier, timeout flag) + partials + block aggregates
     int grid_move;        // CTAs of the step kernel: one per SM (fewer for tiny N)
     int block_size;       // threads per CTA of the step kernel
-    size_t dyn_smem;      // its dynamic shared memory (CDF staging buffers)
+    size_t dyn_smem;      // its dynamic shared memory (math tables, CDF staging buffers, slab records)
+    int slab_doubles;     // doubles of shared memory for the slab records
     int64_t t_host;       // steps launched so far (the device needs no other notion of time)
     bool pdl, coop;       // launch attributes in use (programmatic dependent launch, cooperative)
     bool timed;           // inside smcb_filter_step_timed: plain serialised launches
@@ -1277,6 +1497,7 @@ static int bind_one(smcb_filter *f) {
     f->launch_publish = launch_publish_t<FK>;
     f->block_size = StepCfg<M>::BS;
     f->dyn_smem = StepCfg<M>::dyn_smem;
+    f->slab_doubles = StepCfg<M>::kSlabDoubles;
     SMCB_CUDA(cudaFuncSetAttribute(k_step<M, FK, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)StepCfg<M>::dyn_smem));
     SMCB_CUDA(cudaFuncSetAttribute(k_init<M, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMathTabBytes));

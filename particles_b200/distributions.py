@@ -20,9 +20,13 @@ HALFLOG2PI = 0.5 * np.log(2.0 * np.pi)
 
 
 def _split(v):
-    """scalar-or-array argument -> (device tensor or None, scalar)"""
+    """scalar-or-array argument -> (device tensor or None, scalar).  A size-1 array or tensor is a scalar that
+    broadcasts -- ``StateSpaceModel.simulate`` returns observations of shape (1,), and NumPy broadcasts
+    ``data[t]`` against the (N,) particles."""
     if isinstance(v, torch.Tensor):
-        return (as_device(v) if v.ndim > 0 else None), (float(v) if v.ndim == 0 else 0.0)
+        if v.numel() == 1:
+            return None, float(v.reshape(-1)[0].item())
+        return as_device(v), 0.0
     if isinstance(v, np.ndarray) and v.ndim > 0 and v.size > 1:
         return as_device(v), 0.0
     return None, float(np.asarray(v).reshape(-1)[0])
@@ -60,9 +64,13 @@ class Normal(LocScaleDist):
     """N(loc, scale^2) -- particles/distributions.py:267-285."""
 
     def _n(self, size, *arrs):
-        for a in arrs:
-            if a is not None:
-                return a.shape[0]
+        """Common length of the array arguments (scalars broadcast); mismatched lengths are an error, as NumPy's
+        broadcasting would make them."""
+        lens = {int(a.shape[0]) for a in arrs if a is not None}
+        if len(lens) > 1:
+            raise ValueError(f"operands could not be broadcast together with lengths {sorted(lens)}")
+        if lens:
+            return lens.pop()
         return 1 if size is None else int(size)
 
     def rvs(self, size=None, z=None):

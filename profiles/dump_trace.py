@@ -20,22 +20,27 @@ eng = _FusedEngine(sp, n, "systematic", 0.5, 2024)
 eng.step(K)
 torch.cuda.synchronize()
 lib = C.CDLL(_lib.SO_PATH)
-NW = 4 * 256 + 32 * 256
+NW = 8 * 256 + 32 * 256
 buf = (C.c_ulonglong * NW)()
 lib.smcb_debug_trace(buf, NW)
 raw = np.array(buf[:], dtype=np.uint64).astype(np.int64)
-G = int((raw[:4 * 256].reshape(256, 4)[:, 0] > 0).sum())
-a = raw[:4 * 256].reshape(256, 4)[:G]
-w = raw[4 * 256:].reshape(256, 32)[:G]
-t0 = a[:, 0].min()
+G = int((raw[:8 * 256].reshape(256, 8)[:, 0] > 0).sum())
+a = raw[:8 * 256].reshape(256, 8)[:G]
+w = raw[8 * 256:].reshape(256, 32)[:G]
+t0 = a[:, 1].min()                                   # first CTA past the grid dependency
 nw = int((w[0] > 0).sum())
-rec = {"grid": G, "warps": nw, "start_ns": (a[:, 0] - t0).tolist(), "prologue_done_ns": (a[:, 1] - t0).tolist(),
-       "loop_done_ns": (a[:, 2] - t0).tolist(), "smid": a[:, 3].tolist(),
-       "warp_done_ns": (w[:, :nw] - t0).tolist(), "rs_flag_last_step": float(eng.summ.cpu().numpy()[K - 1, 2])}
-ld = np.array(rec["loop_done_ns"]); pr = np.array(rec["prologue_done_ns"]); wd = np.array(rec["warp_done_ns"])
-rec["summary"] = {"grid": G, "start_spread_ns": int(max(rec["start_ns"])), "prologue_done_p50": int(np.median(pr)), "prologue_done_max": int(pr.max()),
-                  "loop_done_min": int(ld.min()), "loop_done_p50": int(np.median(ld)), "loop_done_max": int(ld.max()),
-                  "warp_done_min": int(wd.min()), "warp_done_p50": int(np.median(wd)), "warp_done_max": int(wd.max()),
-                  "within_cta_warp_spread_p50": int(np.median(wd.max(axis=1) - wd.min(axis=1)))}
+names = ["start", "dep_resolved", "prologue_done", "loop_done", "exit"]
+rec = {"grid": G, "warps": nw, "smid": a[:, 5].tolist(), "rs_flag_last_step": float(eng.summ.cpu().numpy()[K - 1, 2])}
+for i, nm in enumerate(names):
+    rec[nm + "_ns"] = (a[:, i] - t0).tolist()
+rec["warp_done_ns"] = (w[:, :nw] - t0).tolist()
+wd = np.array(rec["warp_done_ns"])
+rec["summary"] = {"grid": G}
+for nm in names:
+    v = np.array(rec[nm + "_ns"])
+    rec["summary"][nm] = [int(v.min()), int(np.median(v)), int(v.max())]
+rec["summary"]["prologue_ns_p50"] = int(np.median(np.array(rec["prologue_done_ns"]) - np.array(rec["dep_resolved_ns"])))
+rec["summary"]["warp_done"] = [int(wd.min()), int(np.median(wd)), int(wd.max())]
+rec["summary"]["within_cta_warp_spread_p50"] = int(np.median(wd.max(axis=1) - wd.min(axis=1)))
 print(json.dumps(rec["summary"]))
 json.dump(rec, open(sys.argv[1], "w"))

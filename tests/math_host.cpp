@@ -24,6 +24,9 @@ static inline double __hiloint2double(int hi, int lo) {
     uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; std::memcpy(&v, &b, 8); return v;
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned int __funnelshift_r(unsigned int lo, unsigned int hi, unsigned int sh) {
+    return (unsigned int)((((uint64_t)hi << 32) | lo) >> (sh & 31));
+}
 using std::fma; using std::fmax; using std::sqrt; using std::floor; using std::atan; using std::lgamma;
 using std::log; using std::exp; using std::fabs; using std::cos;
 #include "smcb.h"                 // model / Feynman-Kac ids
@@ -127,7 +130,7 @@ const double *mh_tables() { return g_tables; }
 int mh_table_doubles() { return smcb::kMathTabDoubles; }
 void mh_exp(const double *x, double *y, long n, int kind, int tab) {
     for (long i = 0; i < n; i++) {
-        if (tab) y[i] = kind == 0 ? smcb::texp(x[i]) : smcb::texp_neg(x[i]);
+        if (tab) y[i] = kind == 0 ? smcb::texp(x[i]) : (kind == 1 ? smcb::texp_neg(x[i]) : smcb::texp_sat(x[i]));
         else y[i] = kind == 0 ? smcb::fexp(x[i]) : (kind == 1 ? smcb::fexp_neg(x[i]) : smcb::fexp_mid(x[i]));
     }
 }

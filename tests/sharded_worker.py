@@ -1,5 +1,5 @@
 """torchrun worker: 2+ ranks, one GPU each.  Checks of the particle-sharded fused filter:
- (1) every rank ends with bit-identical summaries (rank-order merge in k_finish);
+ (1) every rank ends with bit-identical summaries (rank-order merge in the step kernel's prologue);
  (2) logLt agrees with a single-GPU run at the same total N within the reference's own
      Monte-Carlo spread (golden_stats);  (3) the number of resampling steps is in range."""
 import os
@@ -46,12 +46,12 @@ def main():
     from particles_b200 import kalman
     ym = [np.asarray(v) for v in g["data/mvlg_seed5_T30"]]
     fk4 = ssm.GuidedPF(ssm=kalman.MVLinearGauss_Guarniero_etal(alpha=0.4, dx=4), data=ym)
-    global_mode_checks([(fk, "systematic", 300, 10), (fk, "stratified", 300, 10), (fk4, "stratified", 30, 3)],
-                       rank, world)
+    fk_apf = ssm.AuxiliaryPF(ssm=ssm.StochVol(), data=fk.data)
+    global_mode_checks([(fk, "systematic", 300, 10), (fk, "stratified", 300, 10), (fk4, "stratified", 30, 3),
+                        (fk_apf, "systematic", 200, 5)], rank, world)
     try:        # combinations that are not built say so
-        ShardedFilter(ssm.fused_spec(ssm.AuxiliaryPF(ssm=ssm.StochVol(), data=fk.data)), 1000, "systematic", 0.5, 1,
-                      rank, world, resampling_mode="global")
-        raise AssertionError("APF + global resampling should raise")
+        ShardedFilter(ssm.fused_spec(fk), 1000, "multinomial", 0.5, 1, rank, world, resampling_mode="global")
+        raise AssertionError("multinomial + global resampling should raise")
     except NotImplementedError:
         pass
     dist.barrier()
