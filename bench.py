@@ -283,6 +283,30 @@ def multi_gpu_parity(table, spec, y, rank, world):
 
 
 
+def workload(args, K):
+    """(label, make_fk(y_list) -> Feynman-Kac object, observations (K, dy), scheme, essrmin, state dim, parity?)
+    for --config: c2 = BASELINE config 2 (the bench); c3i / c3ii = config 3 as SURVEY.md 8(d) splits it."""
+    from particles_b200 import kalman, state_space_models as ssm
+    if args.config == "c2":
+        y = load_data(K).reshape(-1, 1)
+        return ("StochVol bootstrap", lambda yl: ssm.Bootstrap(ssm=ssm.StochVol(), data=yl), y, SCHEME, ESSRMIN, 1, True)
+    import torch
+    torch.manual_seed(0)
+    from particles_b200 import device
+    device.seed(12345)
+    if args.config == "c3i":      # BearingsOnly (IndepProd(Normal, Normal, Dirac, Dirac), d = 4), Bootstrap, stratified
+        m = ssm.BearingsOnly()
+        _, ys = m.simulate(K)
+        y = np.array([np.asarray(v.cpu()).reshape(-1) for v in ys])
+        return ("BearingsOnly bootstrap (d=4)", lambda yl: ssm.Bootstrap(ssm=ssm.BearingsOnly(), data=yl), y,
+                "stratified", ESSRMIN, 4, False)
+    m = kalman.MVLinearGauss_Guarniero_etal(alpha=0.4, dx=4)       # 4-D MvNormal state, optimal (guided) proposal
+    _, ys = m.simulate(K)
+    y = np.array([np.asarray(v.cpu()).reshape(-1) for v in ys])
+    return ("MVLinearGauss (Guarniero et al, dx=4) guided", lambda yl: ssm.GuidedPF(
+        ssm=kalman.MVLinearGauss_Guarniero_etal(alpha=0.4, dx=4), data=yl), y, "stratified", ESSRMIN, 4, False)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -300,16 +324,19 @@ def run_b200(args):
 
     K, W = args.steps, max(args.warmup, 3)
     n = args.n
-    y = load_data(max(K, W))
-    fk = ssm.Bootstrap(ssm=ssm.StochVol(), data=[np.atleast_1d(v) for v in y[:K]])
+    label, make_fk, y, scheme, essrmin, dim, has_ref = workload(args, max(K, W))
+    y_list = [np.asarray(v, dtype=np.float64).reshape(-1) for v in y[:K]]
+    fk = make_fk(y_list)
     spec = ssm.fused_spec(fk)
+    assert spec is not None, "this workload has no fused kernel"
+    b_st, b_rs = 16.0 * dim + 16.0, 16.0 * dim + 40.0 + 16.0      # algorithmic bytes / particle
 
     def make_engine(nsteps, seed):
         sp = dict(spec)
-        sp["data"] = y[:nsteps].reshape(-1, 1).copy()
+        sp["data"] = np.ascontiguousarray(y[:nsteps])
         if world == 1:
-            return _FusedEngine(sp, n, SCHEME, ESSRMIN, seed)
-        return ShardedFilter(sp, n, SCHEME, ESSRMIN, seed, rank, world, resampling_mode=args.resampling_mode)
+            return _FusedEngine(sp, n, scheme, essrmin, seed)
+        return ShardedFilter(sp, n, scheme, essrmin, seed, rank, world, resampling_mode=args.resampling_mode)
 
     def barrier():
         if world > 1:
@@ -358,19 +385,19 @@ def run_b200(args):
         peak, how = hbm_peak()
         # algorithmic bytes of the step kernel: 32 B/particle on a non-resampling step (x, lw in;
         # x', lw' out); 56 B on a resampling one (lw in, cdf out | cdf in, A out, gather x, x', lw' out)
-        n_st, n_rs_k = max(1, kcnt["step"]), kcnt["step_rs"]
-        step_us = 1e3 * kms["step"] / n_st
-        ach = n * 32.0 / (step_us * 1e-6) / 1e9
+        n_st, n_rs_k = kcnt["step"], kcnt["step_rs"]
+        step_us = 1e3 * kms["step"] / n_st if n_st else float("nan")
+        ach = n * b_st / (step_us * 1e-6) / 1e9
         rs_us = 1e3 * kms["step_rs"] / n_rs_k if n_rs_k else None
-        roof = {"bound": "hbm", "kernel": "k_step<StochVol,Bootstrap,systematic>, non-resampling steps",
+        roof = {"bound": "hbm", "kernel": "k_step<%s>, non-resampling steps" % label,
                 "achieved": ach, "peak": peak, "peak_source": how, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu_traffic(), "traffic_source": "committed ncu capture (profiles/)",
                 "avg_launch_us": step_us, "launches": n_st,
-                "algorithmic_bytes_per_particle": {"no_resample": 32, "resample": 56},
+                "algorithmic_bytes_per_particle": {"no_resample": b_st, "resample": b_rs},
                 "resampling_steps": {"launches": n_rs_k, "avg_launch_us": rs_us,
-                                     "achieved": (n * 56.0 / (rs_us * 1e-6) / 1e9) if rs_us else None,
-                                     "frac": (n * 56.0 / (rs_us * 1e-6) / 1e9 / peak) if rs_us else None},
-                "whole_run_frac": (n * (32.0 * n_st + 56.0 * n_rs_k) / ((kms["step"] + kms["step_rs"]) * 1e-3) / 1e9) / peak,
+                                     "achieved": (n * b_rs / (rs_us * 1e-6) / 1e9) if rs_us else None,
+                                     "frac": (n * b_rs / (rs_us * 1e-6) / 1e9 / peak) if rs_us else None},
+                "whole_run_frac": (n * (b_st * n_st + b_rs * n_rs_k) / ((kms["step"] + kms["step_rs"]) * 1e-3) / 1e9) / peak,
                 "share_of_step_time": {k: v / sum(kms.values()) for k, v in kms.items()}}
         try:                                   # secondary bound: fp64 FMA issue, measured on this device now
             import ctypes as C
@@ -391,13 +418,12 @@ def run_b200(args):
     # end-to-end through the public API: host observations in, host summaries out
     e2e = None
     if world == 1:
-        y_host = [np.atleast_1d(v) for v in y[:K]]
+        y_host = y_list
         runs = []
         for rep_ in range(3):                          # whole call repeated; the median is reported
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            pf = pb.SMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y_host), N=n, resampling=SCHEME,
-                        ESSrmin=ESSRMIN, seed=77)
+            pf = pb.SMC(fk=make_fk(y_host), N=n, resampling=scheme, ESSrmin=essrmin, seed=77)
             pf.run()
             ll = pf.logLt                              # forces the device->host read of the result
             torch.cuda.synchronize()
@@ -406,21 +432,22 @@ def run_b200(args):
                 pf._engine.close()
             del pf
         dt = sorted(runs)[1]
-        e2e = {"value": n * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8,
+        e2e = {"value": n * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * int(y.shape[1]),
                "d2h_bytes_per_step": 32, "seconds": dt, "seconds_all_runs": runs, "logLt": ll,
-               "api": "particles_b200.SMC(fk=Bootstrap(StochVol(), data), N).run(); median of 3 whole calls "
+               "h2d_bytes_per_step_note": "the observations (dy doubles per step)",
+               "api": "particles_b200.SMC(fk=<Feynman-Kac model>, N).run(); median of 3 whole calls "
                       "(construction, pinned->device copy of the observations, T steps, device->host read of "
                       "the summaries)"}
 
     if world > 1:       # end to end through the public sharded API, every rank takes part
         from particles_b200.parallel import ShardedSMC
-        y_host = [np.atleast_1d(v) for v in y[:K]]
+        y_host = y_list
         runs = []
         for rep_ in range(3):                          # whole call repeated; the median is reported
             barrier()
             t0 = time.perf_counter()
-            sp = ShardedSMC(fk=ssm.Bootstrap(ssm=ssm.StochVol(), data=y_host), N=n, resampling=SCHEME,
-                            ESSrmin=ESSRMIN, seed=77, resampling_mode=args.resampling_mode)
+            sp = ShardedSMC(fk=make_fk(y_host), N=n, resampling=scheme,
+                            ESSrmin=essrmin, seed=77, resampling_mode=args.resampling_mode)
             sp.run()
             ll = sp.logLt
             barrier()
@@ -430,19 +457,19 @@ def run_b200(args):
             sp._engine.close()
             del sp
         dt = sorted(runs)[1]
-        e2e = {"value": n * world * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8,
+        e2e = {"value": n * world * K / dt, "unit": "particle-steps/s", "h2d_bytes_per_step": 8 * int(y.shape[1]),
                "d2h_bytes_per_step": 32, "seconds": dt, "seconds_all_runs": runs, "logLt": ll,
                "api": "particles_b200.parallel.ShardedSMC(fk=Bootstrap(StochVol(), data), N).run() on every rank; "
                       "median of 3 whole calls, max over ranks"}
     multi = None
     if world > 1:
-        multi = multi_gpu_parity(table, spec, y, rank, world)
+        multi = multi_gpu_parity(table, spec, y, rank, world) if args.config == "c2" else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.config == "c2":
         live = have_live_reference()
         v, wall = cpu_baseline(n, 4, 1, live)
         cpu = {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "reference" if live else "port",
@@ -456,21 +483,23 @@ def run_b200(args):
         "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"StochVol bootstrap filter, N={n} particles per GPU "
-                               f"(global {total_n}), T={K}, systematic resampling, ESSrmin={ESSRMIN} "
-                               "(BASELINE config 2" + (")" if world == 1 else "/4, particle-sharded)"),
+        "config": {"workload": f"{label} filter, N={n} particles per GPU "
+                               f"(global {total_n}), T={K}, {scheme} resampling, ESSrmin={essrmin} "
+                               + {"c2": "(BASELINE config 2" + (")" if world == 1 else "/4, particle-sharded)"),
+                                  "c3i": "(BASELINE config 3, reference model as it is: Bootstrap)",
+                                  "c3ii": "(BASELINE config 3, 4-D MvNormal guided path)"}[args.config],
                    "l2": "working set 4 x 80 MB of fp64 state per GPU > 126 MB L2 (no flush needed)",
                    "resampling_steps": n_rs, "logLt": logLt,
                    "parallelism": "single GPU" if world == 1 else
                    f"particles sharded over {world} GPUs, {args.resampling_mode} resampling"},
         "gpu_launches": launches,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-        "parity": parity_block(K, total_n, logLt, n_rs,
+        "parity": None if not has_ref else parity_block(K, total_n, logLt, n_rs,
                                None if world == 1 or args.resampling_mode == "global" else
                                "island resampling: a different (consistent) estimator from the reference's global "
                                "scheme; logLt parity is statistical"),
     }
-    if multi is not None:
+    if multi is not None and out["parity"] is not None:
         out["parity"]["multi_gpu"] = multi
     print(json.dumps(out))
     if world > 1:
@@ -483,7 +512,10 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
+    ap.add_argument("--n", type=int, default=None, help="particles per GPU (default: 1e7 for c2, 1e6 for c3)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3i", "c3ii"],
+                    help="c2 = BASELINE config 2 (the bench line); c3i / c3ii = config 3: BearingsOnly bootstrap / 4-D "
+                         "MvNormal guided filter, N = 1e6, stratified")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--resampling-mode", default="island", choices=["island", "global"],
                     help="N > 1 GPUs: per-shard resampling with mass carry (default) or one exact global "
@@ -493,6 +525,10 @@ def main():
     args = ap.parse_args()
     global ESSRMIN
     ESSRMIN = args.essrmin
+    if args.n is None:
+        args.n = N_PER_GPU if args.config == "c2" else 1_000_000
+    if args.config != "c2" and args.steps == 1000:
+        args.steps = 500
     if args.impl == "reference":
         run_reference(args)
     else:

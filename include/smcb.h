@@ -114,8 +114,15 @@ int smcb_normal_rvs(smcb_ctx *ctx, const double *loc, double loc0, const double 
 int smcb_normal_logpdf(smcb_ctx *ctx, const double *x, double x0, const double *loc,
                        double loc0, const double *scale, double scale0, double *out,
                        int64_t n);
-/* MvNormal.rvs / logpdf, distributions.py:946-969; SoA (d, n); L = host (d,d) lower
- * Cholesky factor of cov, row-major; loc/scale: array (d, n), or NULL + host vector[d] */
+/* other univariate log-densities (distributions.py): kind 0 Student(df = p0, loc, scale) :417-433, 1 Gamma(a = p0,
+ * rate) :336-356, 2 Laplace(loc, scale) :399-414, 3 Logistic(loc, scale) :381-396; p1 / p2 arrays or scalars as for
+ * Normal; c0 = the host-computed lgamma constant of the density (0 for kinds 2, 3) */
+int smcb_logpdf1(smcb_ctx *ctx, int kind, const double *x, double x0, double p0, double c0, const double *p1,
+                 double p10, const double *p2, double p20, double *out, int64_t n);
+/* MvNormal.rvs / logpdf, distributions.py:946-969; SoA (d, n), d <= 32; L = host (d,d) lower
+ * Cholesky factor of cov, row-major; loc/scale: array (d, n), or NULL + host vector[d].
+ * d <= 8: factor in the kernel parameters, two particles per thread; 8 < d <= 32: factor in shared
+ * memory, one particle per thread (CUDA cores: HBM-bound at every d <= 32, see smcb_api.cu) */
 int smcb_mvnormal_rvs(smcb_ctx *ctx, const double *loc, const double *loc0,
                       const double *scale, const double *scale0, const double *L, int d,
                       const double *z_in, double *out, int64_t n);
@@ -156,6 +163,15 @@ int smcb_logistic_wf_move(smcb_ctx *ctx, int64_t M, int d, int P, const double *
                           const double *L_dev, const double *z_in, const double *u_in,
                           double *theta_out, double *lprior_out, double *llik_out, double *lpost_out,
                           double *pb_out);
+
+/* AdaptiveTempering's control plane on the device (no host round trip inside a tempering step):
+ * next_annealing_epn, smc_samplers.py:876-895: the exponent at which ESS(delta * llik) = alpha * n, by an 11-pass
+ * 16-way bracketing search whose state stays in device memory; out_dev[0] = new exponent (1.0 if the whole step fits) */
+int smcb_next_annealing_epn(smcb_ctx *ctx, const double *llik, int64_t n, double epn, double alpha, double *out_dev);
+/* ArrayRandomWalk.calibrate, smc_samplers.py:617-622 (rs.wmean_and_cov, resampling.py:341-358): L_out (d, d)
+ * row-major = scale * chol(weighted covariance of the rows of theta), d <= 20 */
+int smcb_rw_calibrate(smcb_ctx *ctx, const double *W, const double *theta, int64_t n, int d, double scale,
+                      double *L_out);
 
 /* test hook: the kernels' own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
  * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1)   -- polynomial family;

@@ -60,6 +60,8 @@ PROTOTYPES = {
     "smcb_normal_rvs": (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, C.c_double, c_dp, c_dp, C.c_int64]),
     "smcb_normal_logpdf": (C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, C.c_double, c_dp, C.c_double,
                                      c_dp, C.c_int64]),
+    "smcb_logpdf1": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_double, C.c_double, C.c_double, c_dp, C.c_double, c_dp,
+                               C.c_double, c_dp, C.c_int64]),
     "smcb_mvnormal_rvs": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_int64]),
     "smcb_mvnormal_logpdf": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp,
                                        C.c_int64]),
@@ -73,6 +75,8 @@ PROTOTYPES = {
     "smcb_rw_propose": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_int, c_dp, c_dp, c_dp]),
     "smcb_mh_accept": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                  c_dp, c_dp]),
+    "smcb_next_annealing_epn": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_double, C.c_double, c_dp]),
+    "smcb_rw_calibrate": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_int, C.c_double, c_dp]),
     "smcb_device_math": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int64]),
     "smcb_filter_create": (C.c_int, [C.c_void_p, C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]),
     "smcb_filter_destroy": (C.c_int, [C.c_void_p]),

@@ -788,6 +788,45 @@ extern "C" int smcb_normal_logpdf(smcb_ctx *c, const double *x, double x0, const
     return SMCB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// more univariate log-densities of distributions.py (the ones a state-space model's PY / PX may use): one
+// elementwise kernel, parameters scalar or per-particle arrays as for Normal.
+//   kind 0 Student(df, loc, scale)  distributions.py:417-433  (scipy.stats.t.logpdf)
+//   kind 1 Gamma(a, b)              distributions.py:336-356  (scipy.stats.gamma.logpdf(x, a, scale = 1 / b))
+//   kind 2 Laplace(loc, scale)      distributions.py:399-414
+//   kind 3 Logistic(loc, scale)     distributions.py:381-396
+// p0 is a scalar (df resp. a); its lgamma terms come in as host-computed constants c0.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_logpdf1(int kind, const double *__restrict__ x, double x0, double p0, double c0,
+                                                   const double *__restrict__ p1, double p10,
+                                                   const double *__restrict__ p2, double p20,
+                                                   double *__restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        const double xv = x ? x[i] : x0, a = p1 ? p1[i] : p10, b = p2 ? p2[i] : p20;
+        double r;
+        if (kind == 0) {                  // c0 = gammaln((df+1)/2) - gammaln(df/2) - log(df pi)/2
+            const double z = (xv - a) / b;
+            r = c0 - 0.5 * (p0 + 1.0) * log1p(z * z / p0) - log(b);
+        } else if (kind == 1) {           // a = rate b (array or scalar); c0 = -gammaln(a_shape)
+            r = (xv > 0.0) ? p0 * log(a) + c0 + (p0 - 1.0) * log(xv) - a * xv : -CUDART_INF;
+        } else if (kind == 2) {
+            r = -log(2.0 * b) - fabs(xv - a) / b;
+        } else {
+            const double z = (xv - a) / b;
+            r = -z - 2.0 * log1p(exp(-z)) - log(b);
+        }
+        out[i] = r;
+    }
+}
+
+extern "C" int smcb_logpdf1(smcb_ctx *c, int kind, const double *x, double x0, double p0, double c0, const double *p1,
+                            double p10, const double *p2, double p20, double *out, int64_t n) {
+    SMCB_REQUIRE(c && out && n >= 1 && kind >= 0 && kind <= 3, "smcb_logpdf1: bad argument");
+    LAUNCH(c, k_logpdf1, grid_for(n, kBlock * 4), kBlock, kind, x, x0, p0, c0, p1, p10, p2, p20, out, n);
+    return SMCB_OK;
+}
+
 constexpr int kMaxDim = 8;
 struct MvnParams {
     double L[kMaxDim * kMaxDim];   // lower Cholesky factor, row-major
@@ -874,14 +913,125 @@ static int fill_mvn(MvnParams *P, const double *loc0, const double *scale0, cons
     return SMCB_OK;
 }
 
+// ---------------------------------------------------------------------------
+// 8 < d <= 32: the factor L (8 KB at d = 32) no longer fits the kernel parameters: it is staged in shared memory
+// (with 1 / L_aa next to it), one particle per thread, z kept in registers through fully unrolled, predicated loops.
+// No tensor cores, and that is a measured decision, not an omission: the Cholesky matvec costs d (d + 1) / 2 fp64 FMAs
+// per particle against 16 d bytes of compulsory traffic (loc in, x out) -- (d + 1) / 32 FMA per byte, 1.03 at
+// d = 32 -- while this B200 delivers 17e12 FMA/s (smcb_measure_fp64_peak: 34 TFLOP/s) per 6.5e12 B/s = 2.6 FMA/B.
+// The kernel is HBM-bound at every d <= 32 (profiles/r02_standalone.json), and fp64 DMMA has the same peak rate as
+// DFMA on this part, so a tensor-core formulation could not move either bound.
+// ---------------------------------------------------------------------------
+constexpr int kBigDim = 32;
+
+struct MvnBig {
+    const double *L;        // device: d x d row-major lower factor, then d reciprocals of the diagonal
+    const double *loc0;     // device: d (or NULL)
+    const double *scale0;   // device: d (or NULL)
+    double halflogdet;
+    int d;
+};
+
+template <bool LOGPDF>
+__global__ void __launch_bounds__(kBlock) k_mvn_big(Philox key, uint64_t call, MvnBig P, const double *__restrict__ xin,
+                                                   const double *__restrict__ loc, const double *__restrict__ scale,
+                                                   const double *__restrict__ z_in, double *__restrict__ out, int64_t n) {
+    __shared__ double sL[kBigDim * kBigDim + 3 * kBigDim];
+    const int d = P.d;
+    for (int e = threadIdx.x; e < d * d + d; e += kBlock) sL[e] = P.L[e];
+    double *sInv = sL + d * d, *sLoc = sInv + kBigDim, *sSc = sLoc + kBigDim;
+    for (int e = threadIdx.x; e < d; e += kBlock) { sLoc[e] = P.loc0 ? P.loc0[e] : 0.0; sSc[e] = P.scale0 ? P.scale0[e] : 1.0; }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        double z[kBigDim];
+        if (!LOGPDF) {
+#pragma unroll
+            for (int k = 0; k < kBigDim; k += 2) {
+                if (k < d) {
+                    if (z_in) {
+                        z[k] = z_in[(size_t)k * n + i];
+                        z[k + 1] = (k + 1 < d) ? z_in[(size_t)(k + 1) * n + i] : 0.0;
+                    } else {                       // one Philox block -> components k, k + 1 of particle i
+                        uint32_t r[4];
+                        philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)call,
+                                      ((uint32_t)(call >> 32) << 16) | ((uint32_t)(k >> 1) << 8) | kPurposeApi, key.k0, key.k1, r);
+                        box_muller(r, z[k], z[k + 1]);
+                    }
+                } else { z[k] = 0.0; z[k + 1] = 0.0; }
+            }
+#pragma unroll
+            for (int a = 0; a < kBigDim; a++) {
+                if (a < d) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int b = 0; b < kBigDim; b++)
+                        if (b <= a) acc += z[b] * sL[a * d + b];
+                    const double l = loc ? loc[(size_t)a * n + i] : sLoc[a];
+                    const double s = scale ? scale[(size_t)a * n + i] : sSc[a];
+                    out[(size_t)a * n + i] = l + s * acc;
+                }
+            }
+        } else {
+            double ss = 0.0, logdet = 0.0;
+#pragma unroll
+            for (int a = 0; a < kBigDim; a++) {
+                if (a < d) {
+                    const double l = loc ? loc[(size_t)a * n + i] : sLoc[a];
+                    const double s = scale ? scale[(size_t)a * n + i] : sSc[a];
+                    double acc = (xin[(size_t)a * n + i] - l) / s;
+#pragma unroll
+                    for (int b = 0; b < kBigDim; b++)
+                        if (b < a) acc -= sL[a * d + b] * z[b];
+                    z[a] = acc / sL[a * d + a];
+                    ss += z[a] * z[a];
+                    if (scale) logdet += log(s);
+                } else z[a] = 0.0;
+            }
+            if (!scale) for (int a = 0; a < d; a++) logdet += log(sSc[a]);
+            out[i] = -0.5 * ss - (logdet + P.halflogdet) - (double)d * kHalfLog2Pi;
+        }
+    }
+}
+
+// stage L (+ reciprocal diagonal), loc0, scale0 in the context's workspace (stream-ordered copies)
+static int fill_mvn_big(smcb_ctx *c, MvnBig *P, const double *loc0, const double *scale0, const double *L, int d) {
+    SMCB_REQUIRE(d > kMaxDim && d <= kBigDim, "MvNormal: dimension %d not in [1, %d]", d, kBigDim);
+    SMCB_REQUIRE(L != nullptr, "MvNormal: L is NULL");
+    double h[kBigDim * kBigDim + 3 * kBigDim];
+    double hl = 0.0;
+    for (int a = 0; a < d; a++) {
+        for (int b = 0; b < d; b++) h[a * d + b] = (b <= a) ? L[a * d + b] : 0.0;
+        SMCB_REQUIRE(L[a * d + a] > 0.0, "MvNormal: argument cov must be a (d, d) pos. definite matrix");
+        hl += log(L[a * d + a]);
+        h[d * d + a] = 1.0 / L[a * d + a];
+        h[d * d + d + a] = loc0 ? loc0[a] : 0.0;
+        h[d * d + 2 * d + a] = scale0 ? scale0[a] : 1.0;
+    }
+    double *w = c->ws + 4096;            // clear of the control-plane scratch at the start of the workspace
+    // the workspace copy must not race with a previous call still reading it on the stream
+    SMCB_CUDA(cudaStreamSynchronize(c->stream));
+    SMCB_CUDA(cudaMemcpyAsync(w, h, sizeof(double) * (d * d + 3 * d), cudaMemcpyHostToDevice, c->stream));
+    P->L = w; P->loc0 = w + d * d + d; P->scale0 = w + d * d + 2 * d; P->halflogdet = hl; P->d = d;
+    return SMCB_OK;
+}
+
 extern "C" int smcb_mvnormal_rvs(smcb_ctx *c, const double *loc, const double *loc0,
                                  const double *scale, const double *scale0, const double *L, int d,
                                  const double *z_in, double *out, int64_t n) {
     SMCB_REQUIRE(c && out && n >= 1, "smcb_mvnormal_rvs: bad argument");
+    uint64_t call = z_in ? 0 : c->api_counter++;
+    if (d > kMaxDim) {
+        MvnBig B;
+        int rc = fill_mvn_big(c, &B, loc0, scale0, L, d);
+        if (rc) return rc;
+        LAUNCH(c, k_mvn_big<false>, grid_for(n, kBlock), kBlock, key_of(c->seed), call, B, (const double *)nullptr, loc,
+               scale, z_in, out, n);
+        return SMCB_OK;
+    }
     MvnParams P;
     int rc = fill_mvn(&P, loc0, scale0, L, d);
     if (rc) return rc;
-    uint64_t call = z_in ? 0 : c->api_counter++;
     LAUNCH(c, k_mvn_rvs, grid_for((n + 1) / 2, kBlock * 2), kBlock, key_of(c->seed), call, P, loc, scale,
            z_in, out, n);
     return SMCB_OK;
@@ -891,6 +1041,14 @@ extern "C" int smcb_mvnormal_logpdf(smcb_ctx *c, const double *x, const double *
                                     const double *loc0, const double *scale, const double *scale0,
                                     const double *L, int d, double *out, int64_t n) {
     SMCB_REQUIRE(c && x && out && n >= 1, "smcb_mvnormal_logpdf: bad argument");
+    if (d > kMaxDim) {
+        MvnBig B;
+        int rc = fill_mvn_big(c, &B, loc0, scale0, L, d);
+        if (rc) return rc;
+        LAUNCH(c, k_mvn_big<true>, grid_for(n, kBlock), kBlock, key_of(c->seed), 0ull, B, x, loc, scale,
+               (const double *)nullptr, out, n);
+        return SMCB_OK;
+    }
     MvnParams P;
     int rc = fill_mvn(&P, loc0, scale0, L, d);
     if (rc) return rc;

@@ -115,15 +115,20 @@ static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) 
         a.grid = f->grid_move;
         // slabs of the streaming branch (smcb_step.cuh): records in the (otherwise idle) CDF staging buffers
         const bool apf = d->fk == SMCB_FK_APF || d->fk == SMCB_FK_AUXBOOT;
-        const bool mom = d->moments != nullptr || d->world > 1;
+        const bool mom = d->moments != nullptr;
         a.slab_lane = (!apf && !mom) ? 1 : 0;
         a.slab_stride = a.slab_lane ? 96 : 4 + (apf ? 4 : 0) + (mom ? 2 * d->dim : 0);
         const int64_t cap = f->slab_doubles / a.slab_stride;
-        const int64_t n_iter = (chunk + 32 * SMCB_KU - 1) / (32 * SMCB_KU);
-        int64_t n_small = n_iter / 8;
-        if (n_small > cap / 4) n_small = cap / 4;
-        int64_t slab_it = (n_iter - n_small + (cap - n_small) - 1) / (cap - n_small);
-        if (slab_it < 2) slab_it = 2;
+        const int64_t n_iter = (chunk + f->pairs_per_iteration - 1) / f->pairs_per_iteration;
+        // smallest slab (>= 2 iterations) whose records fit next to a tail of at least ~one single-iteration slab
+        // per warp: n_big + n_small <= cap with n_big = ceil((n_iter - n_small) / slab_it)
+        int64_t slab_it = 2, n_small = 0;
+        for (;; slab_it++) {
+            const int64_t ns = (cap * slab_it - n_iter) / (slab_it - 1) - 1;
+            const int64_t want = n_iter < 32 ? n_iter : 32;
+            if (ns >= want) { n_small = ns < 0 ? 0 : (ns > n_iter / 8 ? n_iter / 8 : ns); break; }
+        }
+        if (n_small > n_iter) n_small = n_iter;
         if (const char *e = getenv("SMCB_SLAB_IT")) { int v = atoi(e); if (v >= slab_it) slab_it = v; }   // experiments
         a.slab_it = (int)slab_it;
         a.slab_small = (int)n_small;

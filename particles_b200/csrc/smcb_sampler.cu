@@ -408,3 +408,234 @@ extern "C" int smcb_mh_accept(smcb_ctx *c, int64_t n, int d, double *theta, doub
             lpost_p, key_of(c->seed), call, u_in, c->ws, c->counters + 2, mean_acc);
     return SMCB_OK;
 }
+
+// ---------------------------------------------------------------------------
+// the control plane of adaptive tempering on the device (no host round trip inside a tempering step)
+// ---------------------------------------------------------------------------
+namespace smcb {
+
+constexpr int kRootWays = 16;          // candidate exponents evaluated per pass
+constexpr int kRootPasses = 11;        // 16^11 > 1e13: the bracket shrinks below brentq's 2e-12 tolerance
+constexpr int kCtlBlock = 256;
+constexpr int kCtlGrid = 148 * 2;
+
+// max of v (NaN-free log-likelihoods): one pass, last block merges
+__global__ void __launch_bounds__(kCtlBlock) k_ctl_max(const double *__restrict__ v, int64_t n, double *partials,
+                                                      unsigned int *ticket, double *out) {
+    __shared__ double s[kCtlBlock / 32];
+    __shared__ bool last;
+    double m = -CUDART_INF;
+    for (int64_t i = (int64_t)blockIdx.x * kCtlBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kCtlBlock)
+        m = fmax(m, v[i]);
+    for (int k = 16; k > 0; k >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, k));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kCtlBlock / 32; w++) m = fmax(m, s[w]);
+        partials[blockIdx.x] = m;
+        __threadfence();
+        last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        double r = -CUDART_INF;
+        for (unsigned int b = 0; b < gridDim.x; b++) r = fmax(r, reinterpret_cast<volatile double *>(partials)[b]);
+        out[0] = r;
+    }
+}
+
+// one pass of the root-find of next_annealing_epn (smc_samplers.py:876-895): ESS(delta * lw) at the kRootWays
+// points delta_j = lo + (hi - lo) (j + 1) / kRootWays, then the bracket [lo, hi] := the sub-interval in which
+// ESS crosses alpha N (ESS is non-increasing in delta).  state = {lo, hi, max lw, done flag, result}.
+__global__ void __launch_bounds__(kCtlBlock) k_ctl_root_pass(const double *__restrict__ lw, int64_t n, double target,
+                                                            double *state, double *partials, unsigned int *ticket,
+                                                            int final_pass) {
+    __shared__ double s_red[kCtlBlock / 32][2 * kRootWays];
+    __shared__ bool last;
+    const double lo = state[0], hi = state[1], M = state[2];
+    if (state[3] != 0.0) return;                                   // already decided (delta = full step)
+    double dj[kRootWays], s[kRootWays], q[kRootWays];
+#pragma unroll
+    for (int j = 0; j < kRootWays; j++) { dj[j] = lo + (hi - lo) * ((double)(j + 1) / kRootWays); s[j] = 0.0; q[j] = 0.0; }
+    for (int64_t i = (int64_t)blockIdx.x * kCtlBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kCtlBlock) {
+        const double a = lw[i] - M;                                // <= 0
+#pragma unroll
+        for (int j = 0; j < kRootWays; j++) {
+            const double e = fexp_neg(dj[j] * a);
+            s[j] += e;
+            q[j] = fma(e, e, q[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kRootWays; j++) {
+        for (int k = 16; k > 0; k >>= 1) {
+            s[j] += __shfl_xor_sync(0xffffffffu, s[j], k);
+            q[j] += __shfl_xor_sync(0xffffffffu, q[j], k);
+        }
+        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][2 * j] = s[j]; s_red[threadIdx.x >> 5][2 * j + 1] = q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kRootWays) {
+        double v = 0.0;
+        for (int w = 0; w < kCtlBlock / 32; w++) v += s_red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * 2 * kRootWays + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ double tot[2 * kRootWays];
+    if (threadIdx.x < 2 * kRootWays) {                             // fixed block order: deterministic
+        double v = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; b++)
+            v += reinterpret_cast<volatile double *>(partials)[(size_t)b * 2 * kRootWays + threadIdx.x];
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // f(delta) = ESS - target; f(lo) >= 0 by construction.  First j with f(delta_j) < 0 brackets the root.
+        int jx = kRootWays;
+        for (int j = 0; j < kRootWays; j++) {
+            const double ess = tot[2 * j] * tot[2 * j] / tot[2 * j + 1];
+            if (ess - target < 0.0) { jx = j; break; }
+        }
+        if (jx == kRootWays && (final_pass & 2)) {                 // first pass, ESS(hi) >= target: the whole step is allowed
+            state[3] = 1.0;
+            state[4] = hi;
+        } else {
+            if (jx == kRootWays) jx = kRootWays - 1;               // (rounding at the bracket's end in a later pass)
+            const double nlo = lo + (hi - lo) * ((double)jx / kRootWays), nhi = lo + (hi - lo) * ((double)(jx + 1) / kRootWays);
+            state[0] = nlo;
+            state[1] = nhi;
+            if (final_pass & 1) state[4] = 0.5 * (nlo + nhi);
+        }
+    }
+}
+
+__global__ void k_ctl_root_finish(const double *st, double epn, double *out) {
+    out[0] = (st[3] != 0.0) ? 1.0 : epn + st[4];
+}
+
+// weighted mean and covariance of the rows of theta (rs.wmean_and_cov, resampling.py:341-358, as
+// ArrayRandomWalk.calibrate uses it), then L = scale * chol(cov): two passes, fixed-order block merges
+template <int PASS>
+__global__ void __launch_bounds__(kCtlBlock) k_ctl_wcov(const double *__restrict__ W, const double *__restrict__ theta,
+                                                       int64_t n, int d, double *work /* [0..d) mean | d x d cov */,
+                                                       double *partials, unsigned int *ticket, double scale,
+                                                       double *L_out) {
+    __shared__ bool last;
+    extern __shared__ double s_acc[];                              // (kCtlBlock/32) x nvals
+    const int nvals = (PASS == 0) ? d + 1 : d * (d + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each WARP walks rows; lane l accumulates the values v = l, l + 32, ... of the row's contribution
+    constexpr int kMaxPerLane = 8;                                 // d <= 20: d (d + 1) / 2 = 210 <= 256
+    double acc[kMaxPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; k++) acc[k] = 0.0;
+    const int64_t wstride = (int64_t)gridDim.x * (kCtlBlock / 32);
+    for (int64_t r = (int64_t)blockIdx.x * (kCtlBlock / 32) + warp; r < n; r += wstride) {
+        const double w = W[r];
+        const double *row = theta + r * d;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; k++) {
+            const int v = lane + 32 * k;
+            if (v < nvals) {
+                if (PASS == 0) acc[k] += (v < d) ? w * row[v] : w;               // sum w x_j | sum w
+                else {
+                    // v -> (a, b), a >= b (row-major lower triangle)
+                    int a_ = (int)((sqrt(8.0 * v + 1.0) - 1.0) * 0.5);
+                    while ((a_ + 1) * (a_ + 2) / 2 <= v) a_++;
+                    while (a_ * (a_ + 1) / 2 > v) a_--;
+                    const int b_ = v - a_ * (a_ + 1) / 2;
+                    acc[k] += w * (row[a_] - work[a_]) * (row[b_] - work[b_]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; k++) {
+        const int v = lane + 32 * k;
+        if (v < nvals) s_acc[warp * nvals + v] = acc[k];
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nvals; v += kCtlBlock) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < kCtlBlock / 32; w2++) t += s_acc[w2 * nvals + v];
+        partials[(size_t)blockIdx.x * nvals + v] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double *tot = s_acc;
+    for (int v = threadIdx.x; v < nvals; v += kCtlBlock) {
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; b++) t += reinterpret_cast<volatile double *>(partials)[(size_t)b * nvals + v];
+        tot[v] = t;
+    }
+    __syncthreads();
+    if (PASS == 0) {
+        for (int j = threadIdx.x; j <= d; j += kCtlBlock) work[j] = (j < d) ? tot[j] / tot[d] : tot[d];     // mean | sum w
+    } else if (threadIdx.x == 0) {
+        const double sw = work[d];
+        double *cov = work + d + 1;                                // d x d, symmetric
+        for (int a_ = 0; a_ < d; a_++)
+            for (int b_ = 0; b_ <= a_; b_++) { const double c = tot[a_ * (a_ + 1) / 2 + b_] / sw; cov[a_ * d + b_] = c; cov[b_ * d + a_] = c; }
+        // Cholesky (numpy.linalg.cholesky, distributions / smc_samplers.py:617-622), then the 2.38 / sqrt(d) scale
+        for (int j = 0; j < d; j++) {
+            double s = cov[j * d + j];
+            for (int k = 0; k < j; k++) s -= L_out[j * d + k] * L_out[j * d + k];
+            const double ljj = sqrt(s);                            // NaN if not positive definite, as LinAlgError would say
+            L_out[j * d + j] = ljj;
+            for (int i = j + 1; i < d; i++) {
+                double t = cov[i * d + j];
+                for (int k = 0; k < j; k++) t -= L_out[i * d + k] * L_out[j * d + k];
+                L_out[i * d + j] = t / ljj;
+            }
+            for (int i = 0; i < j; i++) L_out[i * d + j] = 0.0;
+        }
+        for (int i = 0; i < d * d; i++) L_out[i] *= scale;
+    }
+}
+
+}  // namespace smcb
+
+// next_annealing_epn (smc_samplers.py:876-895) without the host: out_dev[0] = the new exponent.
+// 1 + kRootPasses launches, the bracket lives in the context's workspace.
+extern "C" int smcb_next_annealing_epn(smcb_ctx *c, const double *lw, int64_t n, double epn, double alpha, double *out_dev) {
+    SMCB_REQUIRE(c && lw && out_dev && n >= 1, "smcb_next_annealing_epn: bad argument");
+    SMCB_REQUIRE(epn >= 0.0 && epn <= 1.0 && alpha > 0.0 && alpha < 1.0, "smcb_next_annealing_epn: epn in [0, 1], alpha in (0, 1)");
+    double *state = c->ws;                                         // 8 doubles
+    double *partials = c->ws + 64;
+    const double init[5] = {0.0, 1.0 - epn, 0.0, 0.0, 0.0};
+    SMCB_CUDA(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    const int grid = (int)((n + kCtlBlock - 1) / kCtlBlock < kCtlGrid ? (n + kCtlBlock - 1) / kCtlBlock : kCtlGrid);
+    LAUNCHK(c, k_ctl_max, grid, kCtlBlock, 0, lw, n, partials, c->counters + 8, state + 2);
+    for (int p = 0; p < kRootPasses; p++)
+        LAUNCHK(c, k_ctl_root_pass, grid, kCtlBlock, 0, lw, n, alpha * (double)n, state, partials, c->counters + 9,
+                (p == kRootPasses - 1 ? 1 : 0) | (p == 0 ? 2 : 0));
+    k_ctl_root_finish<<<1, 1, 0, c->stream>>>(state, epn, out_dev);     // result = epn + delta
+    c->launches++;
+    SMCB_CUDA(cudaGetLastError());
+    return SMCB_OK;
+}
+
+// ArrayRandomWalk.calibrate (smc_samplers.py:617-622): L = scale * chol(wcov(W, theta)) on the device
+extern "C" int smcb_rw_calibrate(smcb_ctx *c, const double *W, const double *theta, int64_t n, int d, double scale,
+                                 double *L_out) {
+    SMCB_REQUIRE(c && W && theta && L_out && n >= 1, "smcb_rw_calibrate: bad argument");
+    SMCB_REQUIRE(d >= 1 && d <= 20, "smcb_rw_calibrate: 1 <= d <= 20 (got %d)", d);
+    double *work = c->ws;                                          // mean[d] | sum w | cov[d x d]
+    double *partials = c->ws + 1024;
+    const int grid = (int)((n + 7) / 8 < kCtlGrid ? (n + 7) / 8 : kCtlGrid);
+    const int nv0 = d + 1, nv1 = d * (d + 1) / 2;
+    LAUNCHK(c, k_ctl_wcov<0>, grid, kCtlBlock, (kCtlBlock / 32) * (nv0 > 32 ? nv0 : 32) * sizeof(double), W, theta, n, d,
+            work, partials, c->counters + 10, scale, L_out);
+    LAUNCHK(c, k_ctl_wcov<1>, grid, kCtlBlock, (kCtlBlock / 32) * nv1 * sizeof(double), W, theta, n, d, work, partials,
+            c->counters + 11, scale, L_out);
+    return SMCB_OK;
+}

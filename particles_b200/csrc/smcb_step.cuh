@@ -43,13 +43,28 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 // (measured, profiles/r02a_variants_and_trace.json: with 3 equal CTAs per SM the first retired at 58 us, the
 // last at 89 us, the SM running 8 warps for the final third), so all warps of an SM live in one CTA and pace
 // each other (progress throttle in the streaming loop).
+#ifndef SMCB_KU
+#define SMCB_KU 2                // pairs of particles in flight per thread in the streaming branch (1-D states)
+#endif
+#ifndef SMCB_L2PREF
+#define SMCB_L2PREF 0            // streaming branch: iterations ahead whose input lines are prefetched into L2 (0: off)
+#endif
+#ifndef SMCB_SLAB_RECORDS
+#define SMCB_SLAB_RECORDS 128    // slab records (768 B each) in shared memory: 128 = the 96 KB of the CDF staging buffers
+#endif
+#ifndef SMCB_BS1D
+#define SMCB_BS1D 512            // threads per CTA of the step kernel for 1-D states (one CTA per SM): 16 warps at
+                                 // up to 128 registers beat 24 warps at 80 (80.8 vs 93.2 us per step, profiles/r02f)
+#endif
 template <class M> struct StepCfg {
-    static constexpr int BS = (M::D == 1) ? 768 : 512;
+    static constexpr int BS = (M::D == 1) ? SMCB_BS1D : 512;
+    static constexpr int kU = (M::D == 1) ? SMCB_KU : 1;   // d-dimensional states: one pair per thread (registers, and
+                                                            // a finer work unit for the N = 1e6 runs they are used at)
     static constexpr int kStage = 8 * BS;             // doubles of CDF staged per output tile (2 BS outputs)
     // dynamic shared memory: the math tables (smcb_tables.h, 64 KB), then two CDF slices (resampling branch) which
     // the streaming branch reuses for its slab records
-    static constexpr int kSlabDoubles = 2 * kStage;
-    static constexpr size_t dyn_smem = kMathTabBytes + 2 * kStage * sizeof(double);
+    static constexpr int kSlabDoubles = SMCB_SLAB_RECORDS * 96;   // per-lane slab records of the streaming branch
+    static constexpr size_t dyn_smem = kMathTabBytes + (size_t)(2 * kStage > kSlabDoubles ? 2 * kStage : kSlabDoubles) * sizeof(double);
 };
 
 // S_t: what is known once step t is finalised; st[t & 1]
@@ -102,6 +117,27 @@ struct FilterArgs {
     const double *pX[8][2];
     const double *pcdf[8];
 };
+
+#ifdef SMCB_TRACE
+// per-CTA timeline of the LAST launch of the step kernel: {start, dependency resolved, prologue done, main loop
+// done, exit, smid} in ns (8 words per CTA), then per warp the time its main loop ended
+__device__ unsigned long long g_trace[8 * 256 + 32 * 256];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+    unsigned int r;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+    return r;
+}
+#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[8 * blockIdx.x + (slot)] = gtimer(); } while (0)
+#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
+#else
+#define SMCB_TRACE_MARK(slot) do { } while (0)
+#define SMCB_TRACE_WARP() do { } while (0)
+#endif
 
 __device__ __forceinline__ void wait_epoch(const volatile double *flag, double epoch, int *timeout) {
     const long long t0 = clock64();
@@ -257,7 +293,8 @@ struct StepSmem {
     double red[32 * 16];
     int prog[32];
     int next;                 // next slab / iteration of the streaming branch
-    int pad;
+    int qn;                   // heavy entries queued by the scatter of a scan tile
+    long long q[64][3];
     double peer[8][kMailStride];
     double goff[9], gpi[8];
     double pref[2];
@@ -307,56 +344,28 @@ __device__ __forceinline__ void warp_reduce_to_slab(const Acc<D> &sa, const Lse3
     }
 }
 
-// fold one slab record into a thread accumulator (fixed order: the caller walks the slabs in slab order)
-template <int D, bool APF>
-__device__ __forceinline__ void acc_merge_slab(Acc<D> &acc, Lse3 &aux, bool mom, const double *rec) {
-    {
-        const double bm = rec[0];
-        const double M = (bm > acc.w.m || bm != bm) ? bm : acc.w.m;
-        const double ea = shift_factor_t(acc.w.m, M), eb = shift_factor_t(bm, M);
-        acc.w.s = acc.w.s * ea + rec[1] * eb;
-        acc.w.q = acc.w.q * (ea * ea) + rec[2] * (eb * eb);
-        acc.w.m = M;
-        if (mom) {
-            const int off = APF ? 8 : 4;
-#pragma unroll
-            for (int c = 0; c < D; c++) {
-                acc.sx[c] = acc.sx[c] * ea + rec[off + c] * eb;
-                acc.sxx[c] = acc.sxx[c] * ea + rec[off + D + c] * eb;
-            }
-        }
-    }
-    if (APF) {
-        const double bm = rec[4];
-        const double M = (bm > aux.m || bm != bm) ? bm : aux.m;
-        const double ea = shift_factor_t(aux.m, M), eb = shift_factor_t(bm, M);
-        aux.s = aux.s * ea + rec[5] * eb;
-        aux.q = aux.q * (ea * ea) + rec[6] * (eb * eb);
-        aux.m = M;
-    }
-}
-
-// this CTA's row of the partials of step t: block reduction of the thread accumulators
+// this CTA's row of the partials of step t: the thread accumulators and (streaming branch) the slab records,
+// every thread taking a fixed subset of the records in a fixed order.  Two passes -- block maximum first, then one
+// exponential per record / accumulator -- instead of pairwise merges with two exponentials each.
 template <int D, bool APF, int BS>
-__device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, Acc<D> acc, Lse3 aux,
+__device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, const Acc<D> &acc, const Lse3 &aux,
                                               bool mom, StepSmem &sh, const double *s_slab = nullptr, int n_slab = 0) {
-    if (n_slab > 0) {                       // streaming branch: the slab records, in a fixed order per thread
-        __syncthreads();
-        if (a.slab_lane) {                  // one (m, s, q) per lane and slab: record r = slab * 32 + lane
-            for (int r = threadIdx.x; r < n_slab * 32; r += BS) {
-                const double *rec = s_slab + (size_t)(r >> 5) * a.slab_stride + (r & 31);
-                const double rr[3] = {rec[0], rec[32], rec[64]};
-                acc_merge_slab<D, false>(acc, aux, false, rr);
-            }
-        } else {
-            for (int sl = threadIdx.x; sl < n_slab; sl += BS)
-                acc_merge_slab<D, APF>(acc, aux, mom, s_slab + (size_t)sl * a.slab_stride);
-        }
-    }
+    const bool lane_rec = a.slab_lane != 0;
+    const int n_rec = lane_rec ? n_slab * 32 : n_slab;
+    auto rec_ptr = [&](int r) {
+        return lane_rec ? s_slab + (size_t)(r >> 5) * a.slab_stride + (r & 31) : s_slab + (size_t)r * a.slab_stride;
+    };
+    const int rs_ = lane_rec ? 32 : 1;                    // distance between m, s, q inside a record
+    if (n_slab > 0) __syncthreads();                      // all records are parked
     double mx[2] = {acc.w.m, APF ? aux.m : -CUDART_INF};
+    for (int r = threadIdx.x; r < n_rec; r += BS) {
+        const double *rec = rec_ptr(r);
+        mx[0] = nanmax(mx[0], rec[0]);
+        if (APF && !lane_rec) mx[1] = nanmax(mx[1], rec[4]);
+    }
     block_max_all<2, BS>(mx, sh.red);
-    const double ew = shift_factor(acc.w.m, mx[0]);
-    const double ea = APF ? shift_factor(aux.m, mx[1]) : 0.0;
+    const double ew = shift_factor_t(acc.w.m, mx[0]);
+    const double ea = APF ? shift_factor_t(aux.m, mx[1]) : 0.0;
     double v[4 + 2 * D];
     v[0] = acc.w.s * ew;
     v[1] = acc.w.q * (ew * ew);
@@ -367,7 +376,30 @@ __device__ __forceinline__ void write_partial(const FilterArgs &a, long long t, 
         v[4 + c] = mom ? acc.sx[c] * ew : 0.0;
         v[4 + D + c] = mom ? acc.sxx[c] * ew : 0.0;
     }
-    block_sum_all<4 + 2 * D, BS>(v, sh.red);
+    for (int r = threadIdx.x; r < n_rec; r += BS) {
+        const double *rec = rec_ptr(r);
+        const double e = shift_factor_t(rec[0], mx[0]);
+        v[0] += rec[rs_] * e;
+        v[1] += rec[2 * rs_] * (e * e);
+        if (!lane_rec) {
+            if (APF) {
+                const double e2 = shift_factor_t(rec[4], mx[1]);
+                v[2] += rec[5] * e2;
+                v[3] += rec[6] * (e2 * e2);
+            }
+            if (mom) {
+                const int off = APF ? 8 : 4;
+#pragma unroll
+                for (int c = 0; c < D; c++) { v[4 + c] += rec[off + c] * e; v[4 + D + c] += rec[off + D + c] * e; }
+            }
+        }
+    }
+    if (mom) block_sum_all<4 + 2 * D, BS>(v, sh.red);
+    else {
+        double w4[4] = {v[0], v[1], v[2], v[3]};
+        block_sum_all<4, BS>(w4, sh.red);
+        v[0] = w4[0]; v[1] = w4[1]; v[2] = w4[2]; v[3] = w4[3];
+    }
     if (threadIdx.x == 0) {
         double *p = a.partials + ((size_t)(t & 1) * kMaxStepGrid + blockIdx.x) * kPartStride;
         p[0] = mx[0]; p[1] = v[0]; p[2] = v[1]; p[3] = 0.0;
@@ -397,42 +429,71 @@ __device__ __forceinline__ void merge16(double (&a)[16], const double *b) {
     }
 }
 
-// this shard's statistics of step s from the per-CTA partial rows (mailbox layout, 16 doubles): thread b owns
-// row b; fixed-order block reductions, so every CTA that runs this holds identical bits.  xrow = this thread's
-// (aux max, aux sum) for the CDF prefix.
-template <bool APF, int BS>
-__device__ __forceinline__ void shard_totals(const FilterArgs &a, long long s, bool mom, StepSmem &sh, double (&loc)[16],
-                                             double &xm_row, double &xs_row) {
+// this shard's statistics of step s from the per-CTA partial rows (mailbox layout, 16 doubles).  Warp 0 alone merges
+// the <= 256 rows -- lane l takes rows l, l + 32, ...; maximum first, then one exponential per row; fixed butterfly
+// order -- and parks the 16 numbers in shared memory: one block barrier, and every CTA that runs this holds identical
+// bits.
+template <bool APF>
+__device__ __forceinline__ void shard_totals(const FilterArgs &a, long long s, bool mom, StepSmem &sh, double (&loc)[16]) {
     const int G = a.grid, tid = threadIdx.x;
-    const double *row = a.partials + ((size_t)(s & 1) * kMaxStepGrid + tid) * kPartStride;
-    double pm = -CUDART_INF, ps = 0.0, pq = 0.0, xm = -CUDART_INF, xs = 0.0, xq = 0.0;
-    if (tid < G) {
-        const double2 r0 = __ldcg(reinterpret_cast<const double2 *>(row));
-        pm = r0.x; ps = r0.y; pq = __ldcg(row + 2);
-        if (APF) {
-            const double2 r1 = __ldcg(reinterpret_cast<const double2 *>(row + 4));
-            xm = r1.x; xs = r1.y; xq = __ldcg(row + 6);
-        } else {
-            xm = pm; xs = ps; xq = pq;
+    if (tid < 32) {
+        const double *base = a.partials + (size_t)(s & 1) * kMaxStepGrid * kPartStride;
+        constexpr int kR = kMaxStepGrid / 32;
+        double pm[kR], ps[kR], pq[kR], xm[kR], xs[kR], xq[kR];
+        double mw = -CUDART_INF, ma = -CUDART_INF;
+#pragma unroll
+        for (int i = 0; i < kR; i++) {
+            const int r = tid + 32 * i;
+            pm[i] = -CUDART_INF; ps[i] = 0.0; pq[i] = 0.0; xm[i] = -CUDART_INF; xs[i] = 0.0; xq[i] = 0.0;
+            if (r < G) {
+                const double *row = base + (size_t)r * kPartStride;
+                const double2 r0 = __ldcg(reinterpret_cast<const double2 *>(row));
+                pm[i] = r0.x; ps[i] = r0.y; pq[i] = __ldcg(row + 2);
+                if (APF) {
+                    const double2 r1 = __ldcg(reinterpret_cast<const double2 *>(row + 4));
+                    xm[i] = r1.x; xs[i] = r1.y; xq[i] = __ldcg(row + 6);
+                }
+            }
+            mw = nanmax(mw, pm[i]);
+            if (APF) ma = nanmax(ma, xm[i]);
+        }
+        mw = warp_max_nan(mw);
+        if (APF) ma = warp_max_nan(ma);
+        double v[12];
+#pragma unroll
+        for (int j2 = 0; j2 < 12; j2++) v[j2] = 0.0;
+#pragma unroll
+        for (int i = 0; i < kR; i++) {
+            const int r = tid + 32 * i;
+            const double ew = shift_factor(pm[i], mw);
+            v[0] += ps[i] * ew;
+            v[1] += pq[i] * (ew * ew);
+            if (APF) {
+                const double ea = shift_factor(xm[i], ma);
+                v[2] += xs[i] * ea;
+                v[3] += xq[i] * (ea * ea);
+            }
+            if (mom && r < G) {
+                const double *row = base + (size_t)r * kPartStride + 8;
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[4 + c] += __ldcg(row + c) * ew;
+            }
+        }
+#pragma unroll
+        for (int j2 = 0; j2 < 12; j2++)
+            if (j2 < 4 || mom) v[j2] = warp_sum(v[j2]);
+        if (tid == 0) {
+            double *o = sh.peer[0];               // (not yet in use: the exchange fills it later)
+            o[0] = mw; o[1] = v[0]; o[2] = v[1]; o[3] = 0.0;
+            o[4] = APF ? ma : mw; o[5] = APF ? v[2] : v[0]; o[6] = APF ? v[3] : v[1]; o[7] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; c++) o[8 + c] = v[4 + c];
         }
     }
-    double mx[2] = {pm, xm};
-    block_max_all<2, BS>(mx, sh.red);
-    double v[12];
-    const double ew = shift_factor(pm, mx[0]);
-    v[0] = ps * ew;
-    v[1] = pq * (ew * ew);
-    const double ea = APF ? shift_factor(xm, mx[1]) : 0.0;
-    v[2] = APF ? xs * ea : 0.0;
-    v[3] = APF ? xq * (ea * ea) : 0.0;
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 8; c++) v[4 + c] = (mom && tid < G) ? __ldcg(row + 8 + c) * ew : 0.0;
-    block_sum_all<12, BS>(v, sh.red);
-    loc[0] = mx[0]; loc[1] = v[0]; loc[2] = v[1]; loc[3] = 0.0;
-    loc[4] = APF ? mx[1] : mx[0]; loc[5] = APF ? v[2] : v[0]; loc[6] = APF ? v[3] : v[1]; loc[7] = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; c++) loc[8 + c] = v[4 + c];
-    xm_row = xm; xs_row = xs;
+    for (int j2 = 0; j2 < 16; j2++) loc[j2] = sh.peer[0][j2];
+    __syncthreads();
 }
 
 // exclusive prefixes P_b, P_{b+1} of this CTA over per-CTA values v (thread b holds v_b, 0 beyond the grid):
@@ -471,9 +532,18 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
                                                       bool need_prefix) {
     const long long s = t - 1;
     const int tid = threadIdx.x;
-    const bool mom = writer && (a.moments != nullptr || a.world > 1);
-    double loc[16], xm_row, xs_row;
-    shard_totals<APF, BS>(a, s, mom, sh, loc, xm_row, xs_row);
+    const bool mom = writer && a.moments != nullptr;
+    // S_{s-1}: requested first, needed last
+    StepState prev;
+    prev.logLt = 0.0; prev.log_mean_w = 0.0; prev.nrs = 0; prev.rs_next = 0;
+    if (s >= 1) {
+        const StepState *pp = a.st + ((s - 1) & 1);
+        prev.logLt = __ldcg(&pp->logLt); prev.log_mean_w = __ldcg(&pp->log_mean_w);
+        prev.nrs = __ldcg(&pp->nrs); prev.rs_next = __ldcg(&pp->rs_next);
+    }
+    double loc[16];
+    shard_totals<APF>(a, s, mom, sh, loc);
+    SMCB_TRACE_MARK(6);
     double glob[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) glob[j] = loc[j];
@@ -517,17 +587,11 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
     }
     const Lse3 w{glob[0], glob[1], glob[2]}, x{glob[4], glob[5], glob[6]};
     const Lse3 xl{loc[4], loc[5], loc[6]};
-    StepState prev;
-    prev.logLt = 0.0; prev.log_mean_w = 0.0; prev.nrs = 0; prev.rs_next = 0;
-    if (s >= 1) {
-        const StepState *pp = a.st + ((s - 1) & 1);
-        prev.logLt = __ldcg(&pp->logLt); prev.log_mean_w = __ldcg(&pp->log_mean_w);
-        prev.nrs = __ldcg(&pp->nrs); prev.rs_next = __ldcg(&pp->rs_next);
-    }
     const double N = (double)a.n_global;
     double log_mean, ess, lm_aux, ess_aux;
     weights_scalars(w, N, log_mean, ess);
-    weights_scalars(x, N, lm_aux, ess_aux);
+    if (APF) weights_scalars(x, N, lm_aux, ess_aux);
+    else { lm_aux = log_mean; ess_aux = ess; }
     const int rs_s = prev.rs_next;                                          // did step s resample?
     const bool fresh = (s == 0) || (rs_s != 0);
     const double loglt = fresh ? log_mean : (log_mean - prev.log_mean_w);   // core.py:355-358
@@ -564,11 +628,16 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
             }
         }
     }
+    SMCB_TRACE_MARK(7);
     if (d.rs && need_prefix) {
         // The CTAs own contiguous particle ranges, so their partial sums ARE the tile aggregates of the weight
         // scan: exclusive prefixes P_0 = 0 <= P_1 <= ... <= P_G (fixed order, monotone, the same bits in every
         // CTA), and the scan needs no look-back at all.
-        const double v = (tid < a.grid) ? xs_row * shift_factor(xm_row, d.xm) / d.xs : 0.0;
+        double v = 0.0;
+        if (tid < a.grid) {                      // row tid of the partials: this CTA's (auxiliary) weight mass
+            const double *row = a.partials + ((size_t)(s & 1) * kMaxStepGrid + tid) * kPartStride + (APF ? 4 : 0);
+            v = __ldcg(row + 1) * shift_factor(__ldcg(row), d.xm) / d.xs;
+        }
         cta_prefix<BS>(v, sh, d.p_b, d.p_next);
     }
     return d;
@@ -615,7 +684,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_init(M model, FilterArgs 
     Acc<D> acc;
     acc_init(acc);
     Lse3 aux = lse3_empty();
-    const bool mom = a.moments != nullptr || a.world > 1;
+    const bool mom = a.moments != nullptr;
     const int64_t n = a.n;
     const bool has_next = APF && a.T > 1;
     const bool vec_x = (D == 1) || ((n & 1) == 0);
@@ -671,14 +740,15 @@ struct LoadWeights {
     double m, s;
     M model;
     StepK kprev;   // step t-1 with y_next = data[t]: what logeta(t-1, X) needs
-    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+    struct Raw { double l[8]; double x[8][FkTraits<FK>::apf ? M::D : 1]; };
+    // the loads of 8 consecutive particles (log-weights; states too when logeta needs them) ...
+    __device__ __forceinline__ void fetch(int64_t i0, int64_t n, Raw &r) const {
         constexpr bool APF = FkTraits<FK>::apf;
         constexpr int D = M::D;
-        double l[8], x[8][APF ? D : 1];
         const bool vec_x = (D == 1) || ((ntot & 1) == 0);
         if (i0 + 8 <= n) {
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) { double2 t = ld2(lw + i0 + j); l[j] = t.x; l[j + 1] = t.y; }
+            for (int j = 0; j < 8; j += 2) { double2 t = ld2(lw + i0 + j); r.l[j] = t.x; r.l[j + 1] = t.y; }
             if (APF) {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
@@ -686,10 +756,10 @@ struct LoadWeights {
                     for (int j = 0; j < 8; j += 2) {
                         if (vec_x) {
                             double2 t = ld2(X + (size_t)c * ntot + i0 + j);
-                            x[j][APF ? c : 0] = t.x; x[j + 1][APF ? c : 0] = t.y;
+                            r.x[j][APF ? c : 0] = t.x; r.x[j + 1][APF ? c : 0] = t.y;
                         } else {
-                            x[j][APF ? c : 0] = X[(size_t)c * ntot + i0 + j];
-                            x[j + 1][APF ? c : 0] = X[(size_t)c * ntot + i0 + j + 1];
+                            r.x[j][APF ? c : 0] = X[(size_t)c * ntot + i0 + j];
+                            r.x[j + 1][APF ? c : 0] = X[(size_t)c * ntot + i0 + j + 1];
                         }
                     }
                 }
@@ -697,19 +767,30 @@ struct LoadWeights {
         } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                l[j] = (i0 + j < n) ? lw[i0 + j] : -CUDART_INF;
+                r.l[j] = (i0 + j < n) ? lw[i0 + j] : -CUDART_INF;
                 if (APF) {
 #pragma unroll
-                    for (int c = 0; c < D; c++) x[j][APF ? c : 0] = (i0 + j < n) ? X[(size_t)c * ntot + i0 + j] : 0.0;
+                    for (int c = 0; c < D; c++) r.x[j][APF ? c : 0] = (i0 + j < n) ? X[(size_t)c * ntot + i0 + j] : 0.0;
                 }
             }
         }
+    }
+    // ... and their normalised (auxiliary) weights W = exp(lw - m) * (1 / s)  (resampling.py:223-225; the reference
+    // divides by s: one rounding apart, and the CDF the ancestors are held to is the device's own)
+    __device__ __forceinline__ void weights(const Raw &r, int64_t i0, int64_t n, double (&v)[8]) const {
+        constexpr bool APF = FkTraits<FK>::apf;
+        const double inv_s = 1.0 / s;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            double e = l[j];
-            if (APF) e = fix_nan(e + model_logeta<M>(model, kprev, x[j]));
-            v[j] = (i0 + j < n) ? texp(e - m) / s : 0.0;
+            double e = r.l[j];
+            if (APF) e = fix_nan(e + model_logeta<M>(model, kprev, r.x[j]));
+            v[j] = (i0 + j < n) ? texp(e - m) * inv_s : 0.0;
         }
+    }
+    __device__ __forceinline__ void operator()(int64_t i0, int64_t n, double (&v)[8]) const {
+        Raw r;
+        fetch(i0, n, r);
+        weights(r, i0, n, v);
     }
 };
 
@@ -756,6 +837,108 @@ __device__ __forceinline__ void scan_range(const LOAD &load, int64_t e0, int64_t
         }
         carry = carry_next;
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Offspring counting (systematic / stratified; resampling.py:599-610): while a CTA scans its range it also
+// scatters the ancestors.  With su_k = (u + k) / N the outputs that select entry j are the k with
+// cdf[j-1] < su_k <= cdf[j], i.e. k in [F(cdf[j-1]), F(cdf[j])) where F(c) = #{k : su_k <= c} = floor(c N - u) + 1.
+// F is evaluated in fp64 (one FMA + floor), so a boundary output may land one entry off when c N - u sits within
+// rounding distance of an integer; the move pass VERIFIES every ancestor against the exact su_k the reference
+// computes (the division) and walks to the searchsorted answer, so the result is bit-identical to
+// np.searchsorted(cdf, su) -- the scatter only has to be a good hint that leaves no output unassigned.  Coverage is
+// gap-free by construction: consecutive threads / tiles / CTAs use the SAME fp64 expression for the shared boundary.
+// Stratified uses u = 0 (the hint is searchsorted(cdf, k / N) <= the answer; the move pass walks forward).
+// ---------------------------------------------------------------------------
+struct Scatter {
+    long long *A;
+    double Nd, u;
+    long long n_out;
+    // floor(c N - u) + 1 as rint(c N - u + 1/2) through the magic-number sum (no conversion instruction); the
+    // half-way cases differ from the floor -- it is a hint, the move pass decides
+    __device__ __forceinline__ long long F(double c) const {
+        const double t = fma(c, Nd, 0.5 - u) + kRintMagic;            // c in [0, 1], N < 2^50 (the magic constant's ulp is 1:
+                                                                      // it must be added AFTER the fraction is formed)
+        const long long k = (long long)(((unsigned long long)(__double2hiint(t) & 0xFFFFF) << 32) |
+                                        (unsigned int)__double2loint(t)) - (1ll << 51);
+        return k < 0 ? 0 : (k > n_out ? n_out : k);
+    }
+};
+
+constexpr int kHeavy = 48;          // offspring of one entry above which the whole CTA fills them cooperatively
+constexpr int kHeavyQ = 64;
+
+template <int BS, class LOAD>
+__device__ __forceinline__ void scan_scatter_range(const LOAD &load, int64_t e0, int64_t e1, double p_b, double p_next,
+                                                   double *out, double *s_warp, const Scatter &sc, bool last_cta,
+                                                   StepSmem &sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kTile = BS * kScanItems;
+    double carry = 0.0;
+    typename LOAD::Raw nxt;                                   // the next tile's loads are in flight while this one is scanned
+    load.fetch(e0 + (int64_t)tid * kScanItems, e1, nxt);
+    for (int64_t base0 = e0; base0 < e1; base0 += kTile) {
+        const int64_t i0 = base0 + (int64_t)tid * kScanItems;
+        const bool last_tile = base0 + kTile >= e1;
+        double r[kScanItems];
+        const typename LOAD::Raw cur = nxt;
+        if (!last_tile) load.fetch(i0 + kTile, e1, nxt);
+        load.weights(cur, i0, e1, r);
+#pragma unroll
+        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
+        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
+        if (lane == 31) s_warp[warp] = iw;
+        if (tid == 0) sh.qn = 0;
+        __syncthreads();
+        double woff = 0.0, total = 0.0;
+#pragma unroll
+        for (int w = 0; w < BS / 32; w++) {
+            if (w < warp) woff = woff + s_warp[w];
+            total = total + s_warp[w];
+        }
+        const double incl = woff + iw;
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double b_i = fmin(p_b + carry, p_next);         // base of this sub-tile
+        const double carry_next = carry + total;
+        const double b_next = fmin(p_b + carry_next, p_next); // base of the next one
+        const double tb = b_i + excl;
+        const double cap = fmin(b_i + incl, b_next);
+        double o[kScanItems];
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) o[j] = fmin(tb + r[j], cap);
+        if (i0 + kScanItems <= e1) {
+            store_items(out, i0, o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++)
+                if (i0 + j < e1) out[i0 + j] = o[j];
+        }
+        // ---- scatter: this thread's 8 entries cover the outputs [F(tb), F(end)), `end` being the next thread's tb.
+        // ONE hint per output -- the first of the 8 entries; the move pass finds the entry inside the block with 8
+        // comparisons -- so the scan pays two F() and one store loop per thread instead of eight.
+        if (i0 < e1) {
+            const bool tail_thread = (i0 + kScanItems >= e1);       // owns the last entry of the CTA's range
+            double endv = (tid == BS - 1 || tail_thread) ? b_next : b_i + incl;
+            if (last_tile && tail_thread) endv = p_next;
+            long long ks = (blockIdx.x == 0 && i0 == 0) ? 0 : sc.F(tb);      // output 0 belongs to the first entry
+            long long ke = (last_tile && tail_thread && last_cta) ? sc.n_out : sc.F(endv);
+            ke = ke < ks ? ks : ke;
+            if (ke - ks > kHeavy) {
+                const int q = atomicAdd(&sh.qn, 1);
+                if (q < kHeavyQ) { sh.q[q][0] = ks; sh.q[q][1] = ke; sh.q[q][2] = i0; ks = ke; }
+            }
+            for (long long k = ks; k < ke; k++) sc.A[k] = i0;
+        }
+        carry = carry_next;
+        __syncthreads();
+        const int nq = sh.qn < kHeavyQ ? sh.qn : kHeavyQ;         // heavy entries: all threads fill their offspring
+        for (int q = 0; q < nq; q++) {
+            const long long ks = sh.q[q][0], ke = sh.q[q][1], jj = sh.q[q][2];
+            for (long long k = ks + tid; k < ke; k += BS) sc.A[k] = jj;
+        }
+        if (nq > 0) __syncthreads();
     }
 }
 
@@ -821,34 +1004,15 @@ __device__ __forceinline__ int shard_of(const double *goff, const double *gpi, i
 // the step kernel: resample_move + reweight_particles (+ compute_summaries of the previous step)
 // (core.py:323-367)
 // ---------------------------------------------------------------------------
-#ifndef SMCB_KU
-#define SMCB_KU 2
-#endif
 #ifndef SMCB_THROTTLE
 #define SMCB_THROTTLE 1          // SMCB_SCHED 0: iterations a warp may run ahead of the slowest warp of its CTA (0: off)
 #endif
+#ifndef SMCB_PREFETCH
+#define SMCB_PREFETCH 1          // streaming branch, 1-D states: request the next iteration's inputs one iteration ahead
+                                 // (77.5 vs 80.8 us at 512 threads; at 768 threads / 80 registers it spills: 120 us)
+#endif
 #ifndef SMCB_SCHED
 #define SMCB_SCHED 2             // 0 static + throttle, 1 dynamic (experiment, order-dependent sums), 2 dynamic slabs
-#endif
-#ifdef SMCB_TRACE
-// per-CTA timeline of the LAST launch of the step kernel: {start, dependency resolved, prologue done, main loop
-// done, exit, smid} in ns (8 words per CTA), then per warp the time its main loop ended
-__device__ unsigned long long g_trace[8 * 256 + 32 * 256];
-__device__ __forceinline__ unsigned long long gtimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ unsigned int smid() {
-    unsigned int r;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(r));
-    return r;
-}
-#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[8 * blockIdx.x + (slot)] = gtimer(); } while (0)
-#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
-#else
-#define SMCB_TRACE_MARK(slot) do { } while (0)
-#define SMCB_TRACE_WARP() do { } while (0)
 #endif
 
 template <class M, int FK, int SCHEME>
@@ -889,7 +1053,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     const int64_t n = a.n;
     const double *zin = a.z_in ? a.z_in + (size_t)t * NZ * n : nullptr;
     const bool last_apf = APF && (t + 1 < a.T);
-    const bool mom = a.moments != nullptr || a.world > 1;
+    const bool mom = a.moments != nullptr;
     const bool vec_x = (D == 1) || ((n & 1) == 0);     // SoA component rows are 16-byte aligned
     int64_t pstart, pend;
     cta_range(a, pstart, pend);
@@ -943,7 +1107,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     if (!rs) {
         // A = arange(N), Xp = X (core.py:335-336): pure streaming pass.  Work unit = one "iteration" of a warp:
         // kU x 32 consecutive pairs (kU coalesced 512-byte rows per array), kU pairs in flight per thread.
-        constexpr int kU = SMCB_KU;
+        constexpr int kU = StepCfg<M>::kU;
         constexpr int kIt = 32 * kU;                                          // pairs per iteration
         const int lane = threadIdx.x & 31;
         const int npl = (int)(pend - pstart);                                 // pairs of this CTA (< 2^31)
@@ -958,63 +1122,82 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
         double *__restrict__ lwo_c = lwo + 2 * pstart;
         double *__restrict__ Xo_c = Xo + 2 * pstart;
         const uint64_t gpair0 = (uint64_t)((a.index_offset >> 1) + pstart);
-        // one iteration: pairs (relative to pstart) i * kIt + u * 32 + lane
+        // one iteration: pairs (relative to pstart) i * kIt + u * 32 + lane.  Loads and arithmetic are separate so
+        // that the inputs of the NEXT iteration can be requested before the current one is computed.
+        struct In { double base[kU][2]; double xp[kU][2][D]; };
+        auto load_full = [&](int i, In &in) {
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int o2 = 2 * (i * kIt + u * 32 + lane);
+                const double2 tl = ld2(lwi_c + o2);
+                in.base[u][0] = tl.x; in.base[u][1] = tl.y;
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+                    const double2 tx = ld2(Xi_c + (size_t)c * n + o2);
+                    in.xp[u][0][c] = tx.x; in.xp[u][1][c] = tx.y;
+                }
+            }
+        };
+        auto compute_full = [&](int i, const In &in, Acc<D> &ac, Lse3 &ax) {
+            double l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
+#if SMCB_L2PREF
+            {   // pull the inputs some iterations ahead of the CTA's front into L2 (one line per lane, 1-D states)
+                const int ip = i + SMCB_L2PREF;
+                constexpr int kLines = kIt / 8;               // 128-byte lines per array and iteration
+                if (D == 1 && ip < n_full && lane < 2 * kLines) {
+                    const double *src = (lane < kLines ? lwi_c : Xi_c) + 2 * ((size_t)ip * kIt) + (size_t)(lane % kLines) * 16;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+                }
+            }
+#endif
+            bool odd = false;                                 // some value is +-inf / NaN (integer test)
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int prel = i * kIt + u * 32 + lane;
+                double z[2][NZ];
+#pragma unroll
+                for (int c = 0; c < NZ; c++)
+                    normal_pair_tab(a.key, gpair0 + (uint64_t)prel, (uint32_t)t, (uint32_t)c, z[0][c], z[1][c]);
+#pragma unroll
+                for (int j2 = 0; j2 < 2; j2++) {
+                    double d;
+                    model_move<M, FK>(model, k, in.xp[u][j2], z[j2], x[2 * u + j2], d);
+                    l[2 * u + j2] = in.base[u][j2] + d;                   // Weights.add, resampling.py:241-244
+                    odd |= nonfinite(l[2 * u + j2]);
+                    if (APF) {
+                        av[APF ? 2 * u + j2 : 0] = last_apf ? l[2 * u + j2] + model_logeta<M>(model, k, x[2 * u + j2])
+                                                            : -CUDART_INF;
+                        odd |= nonfinite(av[APF ? 2 * u + j2 : 0]);
+                    }
+                }
+            }
+            if (odd) {                                        // rare: NaN -> -inf (resampling.py:220)
+#pragma unroll
+                for (int q = 0; q < 2 * kU; q++) {
+                    l[q] = fix_nan(l[q]);
+                    if (APF) av[APF ? q : 0] = fix_nan(av[APF ? q : 0]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int o2 = 2 * (i * kIt + u * 32 + lane);
+#pragma unroll
+                for (int c = 0; c < D; c++) st2(Xo_c + (size_t)c * n + o2, x[2 * u][c], x[2 * u + 1][c]);
+                st2(lwo_c + o2, l[2 * u], l[2 * u + 1]);
+            }
+            if (!odd) {
+                acc_add_batch<2 * kU, D, true>(ac, l, x, mom);
+            } else {
+                acc_add_batch<2 * kU, D, false>(ac, l, x, mom);
+            }
+            if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(ax, av);
+        };
         auto iteration = [&](int i, Acc<D> &ac, Lse3 &ax) {
             double l[2 * kU], av[APF ? 2 * kU : 1], x[2 * kU][D];
             if (fast_ok && i < n_full) {
-                double xp[kU][2][D], base[kU][2];
-#pragma unroll
-                for (int u = 0; u < kU; u++) {                    // all loads first (MLP)
-                    const int o2 = 2 * (i * kIt + u * 32 + lane);
-                    const double2 tl = ld2(lwi_c + o2);
-                    base[u][0] = tl.x; base[u][1] = tl.y;
-#pragma unroll
-                    for (int c = 0; c < D; c++) {
-                        const double2 tx = ld2(Xi_c + (size_t)c * n + o2);
-                        xp[u][0][c] = tx.x; xp[u][1][c] = tx.y;
-                    }
-                }
-                bool odd = false;                                 // some value is +-inf / NaN (integer test)
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int prel = i * kIt + u * 32 + lane;
-                    double z[2][NZ];
-#pragma unroll
-                    for (int c = 0; c < NZ; c++)
-                        normal_pair_tab(a.key, gpair0 + (uint64_t)prel, (uint32_t)t, (uint32_t)c, z[0][c], z[1][c]);
-#pragma unroll
-                    for (int j2 = 0; j2 < 2; j2++) {
-                        double d;
-                        model_move<M, FK>(model, k, xp[u][j2], z[j2], x[2 * u + j2], d);
-                        l[2 * u + j2] = base[u][j2] + d;                      // Weights.add, resampling.py:241-244
-                        odd |= nonfinite(l[2 * u + j2]);
-                        if (APF) {
-                            av[APF ? 2 * u + j2 : 0] = last_apf ? l[2 * u + j2] + model_logeta<M>(model, k, x[2 * u + j2])
-                                                                : -CUDART_INF;
-                            odd |= nonfinite(av[APF ? 2 * u + j2 : 0]);
-                        }
-                    }
-                }
-                if (odd) {                                        // rare: NaN -> -inf (resampling.py:220)
-#pragma unroll
-                    for (int q = 0; q < 2 * kU; q++) {
-                        l[q] = fix_nan(l[q]);
-                        if (APF) av[APF ? q : 0] = fix_nan(av[APF ? q : 0]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int o2 = 2 * (i * kIt + u * 32 + lane);
-#pragma unroll
-                    for (int c = 0; c < D; c++) st2(Xo_c + (size_t)c * n + o2, x[2 * u][c], x[2 * u + 1][c]);
-                    st2(lwo_c + o2, l[2 * u], l[2 * u + 1]);
-                }
-                if (!odd) {
-                    acc_add_batch<2 * kU, D, true>(ac, l, x, mom);
-                } else {
-                    acc_add_batch<2 * kU, D, false>(ac, l, x, mom);
-                }
-                if (APF) lse3_add_batch<(APF ? 2 * kU : 1)>(ax, av);
+                In in;
+                load_full(i, in);
+                compute_full(i, in, ac, ax);
                 return;
             }
             // general path: ragged end of the range, the odd last particle, injected normals, odd SoA stride
@@ -1103,21 +1286,44 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
         n_slab = n_big + n_small;
         double *s_slab = s_stage;
         const bool lane_rec = a.slab_lane != 0;
-        for (;;) {
-            int sl = 0;
-            if (lane == 0) sl = atomicAdd(&sh.next, 1);
-            sl = __shfl_sync(0xffffffffu, sl, 0);
-            if (sl >= n_slab) break;
-            const int i0 = sl < n_big ? sl * slab_it : it_small0 + (sl - n_big);
+        auto grab = [&]() {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(&sh.next, 1);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+        auto first_it = [&](int sl) { return sl < n_big ? sl * slab_it : it_small0 + (sl - n_big); };
+        // software pipeline (1-D states): the inputs of the next iteration -- of this slab, or of the slab the warp
+        // takes next -- are requested before the current iteration's arithmetic starts
+        constexpr bool PREF = (D == 1) && (SMCB_PREFETCH != 0);
+        int sl = grab();
+        In pre;
+        bool have = false;
+        if (PREF && sl < n_slab && fast_ok && first_it(sl) < n_full) { load_full(first_it(sl), pre); have = true; }
+        while (sl < n_slab) {
+            const int i0 = first_it(sl);
             const int rem = it_small0 - i0;
             const int cnt = sl < n_big ? (rem < slab_it ? rem : slab_it) : 1;
             Acc<D> sa;
             acc_init(sa);
             Lse3 sx = lse3_empty();
-            for (int k_ = 0; k_ < cnt; k_++) iteration(i0 + k_, sa, sx);
+            int nsl = n_slab;
+            for (int k_ = 0; k_ < cnt; k_++) {
+                const int i = i0 + k_;
+                In cur;
+                const bool cur_have = have;
+                if (PREF && have) cur = pre;
+                int inext = -1;
+                if (k_ + 1 < cnt) inext = i + 1;
+                else { nsl = grab(); if (nsl < n_slab) inext = first_it(nsl); }
+                have = false;
+                if (PREF && inext >= 0 && fast_ok && inext < n_full) { load_full(inext, pre); have = true; }
+                if (PREF && cur_have) compute_full(i, cur, sa, sx);
+                else iteration(i, sa, sx);
+            }
             double *rec = s_slab + (size_t)sl * a.slab_stride;
             if (lane_rec) { rec[lane] = sa.w.m; rec[32 + lane] = sa.w.s; rec[64 + lane] = sa.w.q; }
             else warp_reduce_to_slab<D, APF>(sa, sx, mom, rec, lane);
+            sl = nsl;
         }
 #endif
         SMCB_TRACE_WARP();
@@ -1125,6 +1331,14 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
         // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
         constexpr int kBarriers = (SCHEME == SMCB_RS_MULTINOMIAL) ? 2 : 1;     // grid barriers per resampling step
         unsigned long long bar_target = (unsigned long long)gridDim.x * ((unsigned long long)dec.nrs_prev * kBarriers);
+        const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
+        double u_sys = 0.0;
+        if (SCHEME == SMCB_RS_SYSTEMATIC) {
+            if (uin) u_sys = uin[0];
+            else { double u1; uniform_pair(a.key, 0ull, (uint32_t)t, kPurposeUniform, u_sys, u1); }
+        }
+        constexpr bool kCount = (SCHEME != SMCB_RS_MULTINOMIAL);      // offspring counting (local resampling only)
+        const bool count_path = kCount && !a.rs_global;
         {
             LoadWeights<M, FK> load;
             load.lw = a.lw[cur];
@@ -1135,7 +1349,13 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             load.model = model;
             load.kprev = kprev;
             const int64_t e1 = 2 * pend < n ? 2 * pend : n;
-            scan_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp);
+            if (count_path) {
+                Scatter sc{a.A, (double)n, (SCHEME == SMCB_RS_SYSTEMATIC) ? u_sys : 0.0, (long long)n};
+                scan_scatter_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp, sc,
+                                       blockIdx.x == gridDim.x - 1, sh);
+            } else {
+                scan_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp);
+            }
         }
         if (SCHEME == SMCB_RS_MULTINOMIAL) {
             spacings_pass1<BS>(a, t, sh);
@@ -1143,17 +1363,13 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             grid_barrier(a, bar_target);
             spacings_pass2<BS>(a, sh, s_warp);
         }
+        SMCB_TRACE_MARK(6);                                // (resampling step: scan + scatter done)
         bar_target += gridDim.x;
         grid_barrier(a, bar_target);
-        const double *uin = a.u_in ? a.u_in + (size_t)t * (n + 1) : nullptr;
-        double u_sys = 0.0;
-        if (SCHEME == SMCB_RS_SYSTEMATIC) {
-            if (uin) u_sys = uin[0];
-            else { double u1; uniform_pair(a.key, 0ull, (uint32_t)t, kPurposeUniform, u_sys, u1); }
-        }
+        SMCB_TRACE_MARK(7);                                // (grid barrier passed)
         // shared tail of both searches: gather the ancestors' states, restart weights, propagate
         auto finish_pair = [&](int64_t p, const double *X0, const double *X1, int64_t a0, int64_t a1, long long g0,
-                               long long g1) {
+                               long long g1, bool write_A = true) {
             double xp[2][D], base[2], x[2][D];
 #pragma unroll
             for (int c = 0; c < D; c++) {                // Xp = X[A], component-wise (SoA)
@@ -1166,14 +1382,139 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             } else {     // Weights() then add(delta): lw = 0 + delta (shard mass if sharded)
                 base[0] = reset_c; base[1] = reset_c;
             }
-            if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(g0, g1);
-            else a.A[2 * p] = g0;
+            if (write_A) {
+                if (2 * p + 1 < n) *reinterpret_cast<longlong2 *>(a.A + 2 * p) = make_longlong2(g0, g1);
+                else a.A[2 * p] = g0;
+            }
             double l[2], av[2];
-            do_pair(p, xp, base, x, l, av);
-            acc_add_batch<2, D>(acc, l, x, mom);
+            if (zin == nullptr && vec_x && 2 * p + 1 < n) {       // complete pair, device normals: no bounds tests
+                double z[2][NZ];
+#pragma unroll
+                for (int c = 0; c < NZ; c++)
+                    normal_pair_tab(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, (uint32_t)c, z[0][c], z[1][c]);
+                bool odd = false;
+#pragma unroll
+                for (int j2 = 0; j2 < 2; j2++) {
+                    double d;
+                    model_move<M, FK>(model, k, xp[j2], z[j2], x[j2], d);
+                    l[j2] = base[j2] + d;
+                    odd |= nonfinite(l[j2]);
+                    if (APF) {
+                        av[j2] = last_apf ? l[j2] + model_logeta<M>(model, k, x[j2]) : -CUDART_INF;
+                        odd |= nonfinite(av[j2]);
+                    }
+                }
+                if (odd) {
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; j2++) { l[j2] = fix_nan(l[j2]); if (APF) av[j2] = fix_nan(av[j2]); }
+                }
+#pragma unroll
+                for (int c = 0; c < D; c++) st2(Xo + (size_t)c * n + 2 * p, x[0][c], x[1][c]);
+                st2(lwo + 2 * p, l[0], l[1]);
+                if (!odd) acc_add_batch<2, D, true>(acc, l, x, mom);
+                else acc_add_batch<2, D, false>(acc, l, x, mom);
+            } else {
+                do_pair(p, xp, base, x, l, av);
+                acc_add_batch<2, D>(acc, l, x, mom);
+            }
             if (APF) lse3_add_batch<2>(aux, av);
         };
-        if (!a.rs_global) {
+        if (count_path) {
+            // move pass of the counting path: every output verifies the scattered ancestor against the exact su_k
+            // (cdf[a-1] < su_k <= cdf[a], i.e. np.searchsorted's answer), walks if the hint is off, then gathers,
+            // propagates and reweights.  No tiles, no block barriers: a pair per thread, strided over the CTA's range.
+            const double M_ = (double)n;
+            // exact answer from any starting point: gallop to a bracket, then bisect (O(log distance) loads)
+            auto settle = [&](long long a0, double su) -> long long {
+                a0 = a0 < 0 ? 0 : (a0 > n - 1 ? n - 1 : a0);
+                long long lo_, hi_;                                  // answer in [lo_, hi_]: cdf[lo_-1] < su, cdf[hi_] >= su or hi_ = n-1
+                if (__ldcg(a.cdf + a0) < su) {                       // go up
+                    long long step = 1;
+                    lo_ = a0 + 1;
+                    hi_ = a0 + 1;
+                    while (hi_ < n - 1 && __ldcg(a.cdf + hi_) < su) { lo_ = hi_ + 1; hi_ += step; step <<= 1; }
+                    if (hi_ > n - 1) hi_ = n - 1;
+                } else {                                             // go down
+                    long long step = 1;
+                    hi_ = a0;
+                    lo_ = a0 - 1;
+                    while (lo_ >= 0 && __ldcg(a.cdf + lo_) >= su) { hi_ = lo_; lo_ -= step; step <<= 1; }
+                    lo_ = lo_ < 0 ? 0 : lo_ + 1;
+                }
+                while (lo_ < hi_) {                                  // first j in [lo_, hi_] with cdf[j] >= su
+                    const long long mid = lo_ + ((hi_ - lo_) >> 1);
+                    if (__ldcg(a.cdf + mid) < su) lo_ = mid + 1; else hi_ = mid;
+                }
+                return lo_;
+            };
+            constexpr int kR = 2;                                   // pairs in flight per thread
+            for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kR * BS) {
+                long long h[kR][2];
+                double su[kR][2], cm[kR][2];
+                bool valid[kR], two[kR], moved[kR];
+#pragma unroll
+                for (int r = 0; r < kR; r++) {                      // hints (scattered by the scan), then su
+                    moved[r] = false;
+                    const int64_t p = p0 + (int64_t)r * BS;
+                    valid[r] = p < pend;
+                    two[r] = valid[r] && (2 * p + 1 < n);
+                    h[r][0] = h[r][1] = 0;
+                    if (two[r]) { const longlong2 hh = __ldcg(reinterpret_cast<const longlong2 *>(a.A + 2 * p)); h[r][0] = hh.x; h[r][1] = hh.y; }
+                    else if (valid[r]) h[r][0] = __ldcg(a.A + 2 * p);
+                }
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int64_t p = p0 + (int64_t)r * BS;
+                    if (SCHEME == SMCB_RS_SYSTEMATIC) {                    // resampling.py:609
+                        su[r][0] = (u_sys + (double)(2 * p)) / M_;
+                        su[r][1] = (u_sys + (double)(2 * p + 1)) / M_;
+                    } else {                                               // resampling.py:602
+                        double u0 = 0.0, u1 = 0.0;
+                        if (valid[r]) {
+                            if (uin) { u0 = uin[2 * p]; u1 = two[r] ? uin[2 * p + 1] : 0.0; }
+                            else uniform_pair(a.key, (uint64_t)((a.index_offset >> 1) + p), (uint32_t)t, kPurposeUniform, u0, u1);
+                        }
+                        su[r][0] = (u0 + (double)(2 * p)) / M_;
+                        su[r][1] = (u1 + (double)(2 * p + 1)) / M_;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {                    // the hint names a block of 8 entries: count inside it
+                        long long hh = h[r][q];
+                        hh = hh < 0 ? 0 : (hh > n - 1 ? n - 1 : hh);
+                        hh &= ~1ll;                                  // (hints are even by construction: 16-byte loads)
+                        const bool on = q == 0 ? valid[r] : two[r];
+                        int cnt = 0;
+                        if (on) {
+#pragma unroll
+                            for (int m = 0; m < 8; m += 2) {
+                                double c_a = 2.0, c_b = 2.0;
+                                // (plain loads: this SM touches these lines for the first time in this launch, after the
+                                // grid barrier, so L1 cannot hold an older copy -- and neighbouring outputs reuse them)
+                                if (hh + m + 1 < n) { const double2 cc = *reinterpret_cast<const double2 *>(a.cdf + hh + m); c_a = cc.x; c_b = cc.y; }
+                                else if (hh + m < n) c_a = a.cdf[hh + m];
+                                cnt += (c_a < su[r][q]) + (c_b < su[r][q]);
+                            }
+                        }
+                        cm[r][q] = (on && hh > 0 && cnt == 0) ? __ldcg(a.cdf + hh - 1) : -1.0;
+                        h[r][q] = hh + cnt;
+                        // inside the block (0 < cnt < 8) the count IS searchsorted's answer; at its edges it must be checked
+                        const bool edge_lo = cnt == 0 && !(cm[r][q] < su[r][q]);
+                        const bool edge_hi = cnt == 8 || hh + cnt > n - 1;
+                        if (on && (edge_lo || edge_hi)) h[r][q] = settle(hh + (cnt == 8 ? 7 : cnt), su[r][q]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    if (!two[r]) h[r][1] = h[r][0];
+                    moved[r] = true;                                 // the hint was a block index: always write the ancestor
+                }
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int64_t p = p0 + (int64_t)r * BS;
+                    if (valid[r]) finish_pair(p, Xi, Xi, h[r][0], h[r][1], h[r][0], h[r][1], moved[r]);
+                }
+            }
+        } else if (!a.rs_global) {
             const double M_ = (double)n;
             const double zlast = (SCHEME == SMCB_RS_MULTINOMIAL) ? __ldcg(a.su + n) : 1.0;
             int64_t lo = -1;
@@ -1405,8 +1746,8 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(FilterArgs a, long long t) 
 template <bool APF>
 __global__ void __launch_bounds__(kTailBlock) k_publish(FilterArgs a, long long s) {
     __shared__ StepSmem sh;
-    double loc[16], xm_row, xs_row;
-    shard_totals<APF, kTailBlock>(a, s, true, sh, loc, xm_row, xs_row);
+    double loc[16];
+    shard_totals<APF>(a, s, true, sh, loc);
     if (threadIdx.x == 0)
         for (int i = 0; i < 16; i++) a.local_stats[i] = loc[i];
 }
@@ -1425,6 +1766,7 @@ struct smcb_filter {
     int block_size;       // threads per CTA of the step kernel
     size_t dyn_smem;      // its dynamic shared memory (math tables, CDF staging buffers, slab records)
     int slab_doubles;     // doubles of shared memory for the slab records
+    int pairs_per_iteration;  // work unit of a warp in the streaming branch
     int64_t t_host;       // steps launched so far (the device needs no other notion of time)
     bool pdl, coop;       // launch attributes in use (programmatic dependent launch, cooperative)
     bool timed;           // inside smcb_filter_step_timed: plain serialised launches
@@ -1498,6 +1840,7 @@ static int bind_one(smcb_filter *f) {
     f->block_size = StepCfg<M>::BS;
     f->dyn_smem = StepCfg<M>::dyn_smem;
     f->slab_doubles = StepCfg<M>::kSlabDoubles;
+    f->pairs_per_iteration = 32 * StepCfg<M>::kU;
     SMCB_CUDA(cudaFuncSetAttribute(k_step<M, FK, SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)StepCfg<M>::dyn_smem));
     SMCB_CUDA(cudaFuncSetAttribute(k_init<M, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMathTabBytes));

@@ -95,6 +95,150 @@ class Normal(LocScaleDist):
         return out
 
 
+class _Univariate(ProbDist):
+    """logpdf through the elementwise kernel smcb_logpdf1 (kinds: 0 Student, 1 Gamma, 2 Laplace, 3 Logistic)."""
+    _kind = None
+
+    def _call(self, x, p0, c0, a, b):
+        xa, x0 = _split(x)
+        aa, a0 = _split(a)
+        ba, b0 = _split(b)
+        lens = {int(v.shape[0]) for v in (xa, aa, ba) if v is not None}
+        if len(lens) > 1:
+            raise ValueError(f"operands could not be broadcast together with lengths {sorted(lens)}")
+        n = lens.pop() if lens else 1
+        ctx = context()
+        out = empty(n)
+        _lib.check(ctx.lib.smcb_logpdf1(ctx.handle, self._kind, ptr(xa), x0, float(p0), float(c0), ptr(aa), a0,
+                                        ptr(ba), b0, ptr(out), n))
+        return out
+
+
+class Student(_Univariate):
+    """Student(df, loc, scale) -- particles/distributions.py:417-433 (scipy.stats.t.logpdf); ``df`` scalar."""
+    _kind = 0
+
+    def __init__(self, df=3.0, loc=0.0, scale=1.0):
+        self.df, self.loc, self.scale = df, loc, scale
+
+    def logpdf(self, x):
+        from scipy.special import gammaln
+        df = float(self.df)
+        c0 = gammaln(0.5 * (df + 1.0)) - gammaln(0.5 * df) - 0.5 * np.log(df * np.pi)
+        return self._call(x, df, c0, self.loc, self.scale)
+
+    def rvs(self, size=None):
+        """loc + scale * z / sqrt(chi2_df / df): the normals from the context's Philox stream, the chi-square
+        from torch's generator (the reference draws through scipy.stats.t.rvs)."""
+        la, l0 = _split(self.loc)
+        sa, s0 = _split(self.scale)
+        n = la.shape[0] if la is not None else (sa.shape[0] if sa is not None else (1 if size is None else int(size)))
+        z = Normal().rvs(size=n)
+        g = torch.distributions.Chi2(torch.tensor(float(self.df), dtype=torch.float64, device=z.device)).sample((n,))
+        t = z / torch.sqrt(g / float(self.df))
+        return (la if la is not None else l0) + (sa if sa is not None else s0) * t
+
+
+class Gamma(_Univariate):
+    """Gamma(a, b), density prop. to x^(a-1) exp(-b x) -- particles/distributions.py:336-356; ``a`` scalar,
+    ``b`` scalar or per-particle array."""
+    _kind = 1
+
+    def __init__(self, a=1.0, b=1.0):
+        self.a, self.b = a, b
+        self.scale = 1.0 / b
+
+    def logpdf(self, x):
+        from scipy.special import gammaln
+        return self._call(x, float(self.a), -gammaln(float(self.a)), self.b, 1.0)
+
+    def rvs(self, size=None):
+        b = as_device(self.b) if isinstance(self.b, (torch.Tensor, np.ndarray)) else \
+            torch.full((1 if size is None else int(size),), float(self.b), dtype=torch.float64, device="cuda")
+        a = torch.full_like(b, float(self.a))
+        return torch.distributions.Gamma(a, b).sample()
+
+
+class Laplace(LocScaleDist, _Univariate):
+    """particles/distributions.py:301-314."""
+    _kind = 2
+
+    def logpdf(self, x):
+        return self._call(x, 0.0, 0.0, self.loc, self.scale)
+
+    def rvs(self, size=None):
+        la, l0 = _split(self.loc)
+        sa, s0 = _split(self.scale)
+        n = la.shape[0] if la is not None else (sa.shape[0] if sa is not None else (1 if size is None else int(size)))
+        u = torch.rand(n, dtype=torch.float64, device="cuda") - 0.5
+        return (la if la is not None else l0) - (sa if sa is not None else s0) * torch.sign(u) * torch.log1p(-2 * u.abs())
+
+
+class Logistic(LocScaleDist, _Univariate):
+    """particles/distributions.py:288-299."""
+    _kind = 3
+
+    def logpdf(self, x):
+        return self._call(x, 0.0, 0.0, self.loc, self.scale)
+
+    def rvs(self, size=None):
+        la, l0 = _split(self.loc)
+        sa, s0 = _split(self.scale)
+        n = la.shape[0] if la is not None else (sa.shape[0] if sa is not None else (1 if size is None else int(size)))
+        u = torch.rand(n, dtype=torch.float64, device="cuda")
+        return (la if la is not None else l0) + (sa if sa is not None else s0) * (torch.log(u) - torch.log1p(-u))
+
+
+class Categorical(ProbDist):
+    """Categorical(p), p (k,) or (N, k) -- particles/distributions.py:598-628."""
+    dtype = np.int64
+
+    def __init__(self, p=None):
+        if p is None:
+            raise ValueError("Categorical: missing argument p")
+        self.p = as_device(p)
+
+    def logpdf(self, x):
+        lp = torch.log(self.p)
+        x = as_device(x, dtype=torch.int64)
+        if lp.ndim == 1:
+            return lp[x]
+        return lp.gather(1, x.reshape(-1, 1).expand(lp.shape[0], 1)).reshape(-1)      # np.choose(x, columns)
+
+    def rvs(self, size=None):
+        from . import resampling as rs
+        if self.p.ndim == 1:                                   # searchsorted(cumsum(p), u)
+            n = 1 if size is None else int(size)
+            u = torch.sort(torch.rand(n, dtype=torch.float64, device="cuda"))
+            out = torch.empty(n, dtype=torch.int64, device="cuda")
+            out[u.indices] = rs.inverse_cdf(u.values, self.p)
+            return out
+        n = self.p.shape[0] if size is None else int(size)
+        u = torch.rand(n, 1, dtype=torch.float64, device="cuda")
+        return (torch.cumsum(self.p[:n], 1) < u).sum(1).clamp_(max=self.p.shape[1] - 1)
+
+
+class MixMissing(ProbDist):
+    """Mixture of ``base_dist`` and 'missing' (NaN) -- particles/distributions.py:819-847."""
+
+    def __init__(self, pmiss=0.10, base_dist=None):
+        self.pmiss, self.base_dist = pmiss, base_dist
+
+    def logpdf(self, x):
+        xd = as_device(x)
+        lp = self.base_dist.logpdf(torch.nan_to_num(xd, nan=0.0) if bool(torch.isnan(xd).any()) else xd)
+        ina = torch.isnan(xd).reshape(-1)
+        if ina.shape[0] == 1:
+            ina = ina.expand(lp.shape[0])
+        return torch.where(ina, torch.full_like(lp, float(np.log(self.pmiss))), lp + float(np.log(1.0 - self.pmiss)))
+
+    def rvs(self, size=None):
+        x = self.base_dist.rvs(size=size)
+        miss = torch.rand(x.shape[0], dtype=torch.float64, device=x.device) < self.pmiss
+        x[miss] = float("nan")
+        return x
+
+
 class Poisson(ProbDist):
     """Poisson(rate) -- particles/distributions.py:519-532 (logpdf on the device; ``rate`` a CUDA
     tensor or scalar, ``x`` the observed count).  scipy evaluates xlogy(k, mu) - gammaln(k+1) - mu."""
@@ -164,7 +308,7 @@ class IndepProd(ProbDist):
 
 
 class MvNormal(ProbDist):
-    """Multivariate Normal -- particles/distributions.py:888-982 (d <= 8 on the device).
+    """Multivariate Normal -- particles/distributions.py:888-982 (d <= 32 on the device).
     ``loc``: (d,) or (N, d); ``scale``: scalar, (d,) or (N, d); ``cov``: (d, d) host array."""
 
     def __init__(self, loc=0.0, scale=1.0, cov=None):

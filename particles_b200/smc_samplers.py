@@ -118,13 +118,14 @@ class ArrayRandomWalk:
     """Gaussian random-walk Metropolis, smc_samplers.py:596-629."""
 
     def calibrate(self, W, x):
+        """smc_samplers.py:617-622: L = 2.38 / sqrt(d) * chol(wcov(W, theta)) -- weighted mean, covariance and the
+        Cholesky factor all on the device (smcb_rw_calibrate), nothing comes back to the host."""
         theta = x.theta
-        d = theta.shape[1]
-        m = (W[:, None] * theta).sum(0) / W.sum()                     # rs.wmean_and_cov, resampling.py:341-358
-        xc = theta - m
-        cov = (xc * W[:, None]).t() @ xc / W.sum()                    # np.cov(aweights=W, ddof=0)
-        L = (2.38 / np.sqrt(d)) * np.linalg.cholesky(cov.cpu().numpy())
-        x.shared["chol_cov"] = as_device(np.ascontiguousarray(L))
+        n, d = theta.shape
+        ctx = context()
+        L = empty(d * d).reshape(d, d)
+        _lib.check(ctx.lib.smcb_rw_calibrate(ctx.handle, ptr(as_device(W)), ptr(theta), n, d, 2.38 / np.sqrt(d), ptr(L)))
+        x.shared["chol_cov"] = L
 
     def step(self, x, target, noise=None):
         """ArrayMetropolis.step (601-611); returns the mean acceptance probability (device scalar)."""
@@ -257,8 +258,18 @@ class Tempering(FKSMCsampler):
 
 
 def next_annealing_epn(epn, alpha, lw):
-    """smc_samplers.py:876-895: the exponent at which ESS(e * lw) = alpha * N; ``essl`` is
-    evaluated on the device, the bracketing root-find (brentq) runs on the host as in the reference."""
+    """smc_samplers.py:876-895: the exponent at which ESS(e * lw) = alpha * N.  The whole bracketing root-find runs on
+    the device (smcb_next_annealing_epn: 16 candidate exponents per pass, 11 passes, bracket < 1e-13); the host reads
+    the one resulting scalar, because the reference keeps the exponents as Python floats in ``shared``."""
+    lw = as_device(lw)
+    ctx = context()
+    out = empty(1)
+    _lib.check(ctx.lib.smcb_next_annealing_epn(ctx.handle, ptr(lw), lw.shape[0], float(epn), float(alpha), ptr(out)))
+    return float(out.item())
+
+
+def next_annealing_epn_host(epn, alpha, lw):
+    """The reference's own formulation (brentq on the host, essl on the device): kept for the parity test."""
     N = lw.shape[0]
 
     def f(e):

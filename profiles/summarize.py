@@ -56,9 +56,9 @@ def mix(fn):
 
 
 out = {}
-for k, label in [("move", "k_move, no-resampling step (config 2's common case)"),
-                 ("movers", "k_move, resampling step (search + gather)"),
-                 ("scan", "k_scan_w, resampling step (weights -> CDF)")]:
+for k, label in [("move", "step kernel, no-resampling step (config 2's common case)"),
+                 ("movers", "step kernel, resampling step (weights -> CDF, grid barrier, search + gather + move)"),
+                 ("scan", "k_scan_w, resampling step (weights -> CDF; round-1 kernels only)")]:
     fn = f"{SRC}/{k}_{TAG}_raw.csv"
     if not os.path.exists(fn):
         continue

@@ -398,6 +398,73 @@ def test_mvnormal_vs_reference(pb, golden):
         dists.MvNormal(loc=np.zeros(2), cov=np.array([[1.0, 2.0], [2.0, 1.0]]))
 
 
+@pytest.mark.parametrize("d", [9, 16, 32])
+def test_mvnormal_large_d_vs_oracle(pb, d):
+    """8 < d <= 32 (factor staged in shared memory, one particle per thread) against the oracle's restatement of
+    distributions.py:888-982 with scipy's triangular solve: logpdf, rvs with injected normals, and the moments of
+    device draws."""
+    from particles_b200 import distributions as dists
+    r = np.random.RandomState(d)
+    B = r.randn(d, d)
+    cov = B @ B.T / d + np.eye(d) * 0.3
+    n = 3001
+    loc, sc = r.randn(n, d), np.exp(r.randn(n, d) * 0.2)
+    x = loc + r.randn(n, d)
+    ref = orc.MvNormal(loc=loc, scale=sc, cov=cov)
+    got = host(dists.MvNormal(loc=dev(loc), scale=dev(sc), cov=cov).logpdf(dev(x)))
+    np.testing.assert_allclose(got, ref.logpdf(x), rtol=1e-11)
+    ref0 = orc.MvNormal(loc=loc[0], scale=1.0, cov=cov)
+    np.testing.assert_allclose(host(dists.MvNormal(loc=loc[0], cov=cov).logpdf(dev(x))), ref0.logpdf(x), rtol=1e-11)
+    z = r.standard_normal((n, d))
+    rv = host(dists.MvNormal(loc=dev(loc), scale=dev(sc), cov=cov).rvs(size=n, z=z))
+    np.testing.assert_allclose(rv, ref.rvs(size=n, z=z), rtol=1e-12, atol=1e-13)
+    pb.seed(5)
+    dr = host(dists.MvNormal(loc=np.zeros(d), cov=cov).rvs(size=200_000))
+    assert dr.shape == (200_000, d)
+    assert np.abs(dr.mean(0)).max() < 0.02 and np.abs(np.cov(dr.T) - cov).max() < 0.03
+    with pytest.raises(ValueError):
+        dists.MvNormal(loc=np.zeros(33), cov=np.eye(33)).rvs(size=4)
+
+
+def test_more_univariate_distributions_vs_scipy(pb):
+    """Student / Gamma / Laplace / Logistic / Categorical / MixMissing (distributions.py:288-433, 598-628, 819-847):
+    logpdf against scipy (what the reference calls), scalar and per-particle parameters; rvs moments."""
+    from scipy import stats
+    from particles_b200 import distributions as dists
+    r = np.random.RandomState(0)
+    n = 5000
+    x, loc, sc = r.randn(n) * 2, r.randn(n), np.exp(r.randn(n) * 0.3)
+    np.testing.assert_allclose(host(dists.Student(df=4.5, loc=dev(loc), scale=dev(sc)).logpdf(dev(x))),
+                               stats.t.logpdf(x, 4.5, loc=loc, scale=sc), rtol=1e-12)
+    np.testing.assert_allclose(host(dists.Student(df=3.0, loc=dev(loc)).logpdf(np.array([0.7]))),
+                               stats.t.logpdf(0.7, 3.0, loc=loc), rtol=1e-12)
+    xg = np.abs(x) + 0.1
+    np.testing.assert_allclose(host(dists.Gamma(a=2.5, b=dev(sc)).logpdf(dev(xg))),
+                               stats.gamma.logpdf(xg, 2.5, scale=1.0 / sc), rtol=1e-12)
+    assert host(dists.Gamma(a=2.0, b=1.0).logpdf(dev(np.array([-1.0, 1.0]))))[0] == -np.inf
+    np.testing.assert_allclose(host(dists.Laplace(loc=dev(loc), scale=0.7).logpdf(dev(x))),
+                               stats.laplace.logpdf(x, loc=loc, scale=0.7), rtol=1e-12)
+    np.testing.assert_allclose(host(dists.Logistic(loc=dev(loc), scale=dev(sc)).logpdf(dev(x))),
+                               stats.logistic.logpdf(x, loc=loc, scale=sc), rtol=1e-11)
+    p = r.dirichlet(np.ones(5), size=n)
+    k = r.randint(0, 5, n)
+    np.testing.assert_allclose(host(dists.Categorical(p=dev(p)).logpdf(dev(k, dtype=torch.int64))),
+                               np.log(p[np.arange(n), k]), rtol=1e-13)
+    np.testing.assert_allclose(host(dists.Categorical(p=p[0]).logpdf(dev(k, dtype=torch.int64))), np.log(p[0][k]), rtol=1e-13)
+    draws = host(dists.Categorical(p=p[0]).rvs(size=200_000))
+    np.testing.assert_allclose(np.bincount(draws, minlength=5) / 200_000, p[0], atol=5e-3)
+    xm = x.copy()
+    xm[::7] = np.nan
+    lp = host(dists.MixMissing(pmiss=0.1, base_dist=dists.Normal(loc=dev(loc), scale=0.5)).logpdf(dev(xm)))
+    want = stats.norm.logpdf(xm, loc=loc, scale=0.5) + np.log(0.9)
+    want[::7] = np.log(0.1)
+    np.testing.assert_allclose(lp, want, rtol=1e-12)
+    t = host(dists.Student(df=5.0, loc=1.0, scale=2.0).rvs(size=400_000))
+    assert abs(t.mean() - 1.0) < 0.02 and abs(t.var() - 4.0 * 5 / 3) < 0.15
+    gm = host(dists.Gamma(a=3.0, b=2.0).rvs(size=400_000))
+    assert abs(gm.mean() - 1.5) < 0.01 and abs(gm.var() - 0.75) < 0.02
+
+
 def test_indepprod_dirac_vs_reference(pb, golden):
     from particles_b200 import state_space_models as ssm
     g = golden

@@ -5,6 +5,7 @@ CPU: the oracle (oracle/samplers_numpy.py) against a seeded run of the LIVE refe
 GPU: the device kernels against the oracle on identical inputs, then full runs against the
 reference's own Monte-Carlo spread."""
 import numpy as np
+import torch
 import pytest
 
 from oracle import samplers_numpy as sp
@@ -104,6 +105,25 @@ def test_rw_proposal_and_accept_vs_oracle():
     assert same.mean() > 0.999                       # a draw within 1e-10 of its threshold may flip
     np.testing.assert_allclose(host(x.theta)[same], ref.theta[same], rtol=1e-9, atol=1e-12)
     assert 0.05 < acc.mean() < 0.95
+
+
+@gpu
+def test_device_root_find_matches_brentq():
+    """next_annealing_epn on the device (16-way bracketing, 11 passes) against the reference's formulation (brentq
+    on the host with the device essl) and against the oracle's NumPy version."""
+    pytest.importorskip("torch")
+    from particles_b200 import smc_samplers as ssp
+    r = np.random.RandomState(7)
+    for n, scale, epn in [(100_000, 40.0, 0.0), (50_001, 300.0, 0.013), (4000, 5.0, 0.4), (20_000, 0.01, 0.2)]:
+        lw = -np.abs(r.randn(n)) * scale - 3.0
+        lwd = torch.from_numpy(lw).cuda()
+        got = ssp.next_annealing_epn(epn, 0.5, lwd)
+        want = ssp.next_annealing_epn_host(epn, 0.5, lwd)
+        assert abs(got - want) <= 1e-9 * max(1.0, want) + 1e-12, (n, got, want)
+        ref = sp.next_annealing_epn(epn, 0.5, lw)
+        assert abs(got - ref) <= 1e-9 * max(1.0, ref) + 1e-11, (n, got, ref)
+        if got < 1.0:       # it IS the root: ESS at the new exponent is alpha N
+            np.testing.assert_allclose(orc.essl((got - epn) * lw), 0.5 * n, rtol=1e-8)
 
 
 @gpu
