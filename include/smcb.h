@@ -173,6 +173,14 @@ int smcb_next_annealing_epn(smcb_ctx *ctx, const double *llik, int64_t n, double
 int smcb_rw_calibrate(smcb_ctx *ctx, const double *W, const double *theta, int64_t n, int d, double scale,
                       double *L_out);
 
+/* the same control plane in pieces, for a tempering run sharded over ranks (the host layer all-reduces between them):
+ * raw ESS sums of one root-find pass; raw weighted-moment sums; the factor from all-reduced sums */
+int smcb_essl_grid(smcb_ctx *ctx, const double *llik, int64_t n, double lo, double hi, const double *max_dev,
+                   double *out32_dev);
+int smcb_wcov_sums(smcb_ctx *ctx, const double *W, const double *theta, int64_t n, int d, const double *mean_dev,
+                   double *out_dev);
+int smcb_chol_from_sums(smcb_ctx *ctx, const double *tri_dev, const double *sw_dev, int d, double scale, double *L_out);
+
 /* test hook: the kernels' own fp64 exp / log / sincos (csrc/smcb_math.cuh) on an array;
  * fn: 0 exp, 1 log (x > 0, normal), 2 sin(2 pi x), 3 cos(2 pi x), x in [0, 1)   -- polynomial family;
  *     4 exp, 5 log, 6 sin(2 pi x), 7 cos(2 pi x), 8 sqrt (x > 0, normal)        -- table family (step kernels) */

@@ -77,6 +77,9 @@ PROTOTYPES = {
                                  c_dp, c_dp]),
     "smcb_next_annealing_epn": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_double, C.c_double, c_dp]),
     "smcb_rw_calibrate": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_int, C.c_double, c_dp]),
+    "smcb_essl_grid": (C.c_int, [C.c_void_p, c_dp, C.c_int64, C.c_double, C.c_double, c_dp, c_dp]),
+    "smcb_wcov_sums": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_int, c_dp, c_dp]),
+    "smcb_chol_from_sums": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_dp]),
     "smcb_device_math": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int64]),
     "smcb_filter_create": (C.c_int, [C.c_void_p, C.POINTER(FilterDesc), C.POINTER(C.c_void_p)]),
     "smcb_filter_destroy": (C.c_int, [C.c_void_p]),

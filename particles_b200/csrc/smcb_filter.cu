@@ -30,6 +30,9 @@ static int smcb_bind_1d(smcb_filter *f) {
 }
 
 static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d);
+#ifdef SMCB_TRACE
+static unsigned long long *g_trace_buf = nullptr;
+#endif
 
 extern "C" int smcb_filter_create(smcb_ctx *c, const smcb_filter_desc *d, smcb_filter **out) {
     SMCB_REQUIRE(c && d && out, "smcb_filter_create: NULL argument");
@@ -82,6 +85,14 @@ static int filter_setup(smcb_filter *f, smcb_ctx *c, const smcb_filter_desc *d) 
     a.partials = reinterpret_cast<double *>(f->mem + kHdr);
     a.blk_agg = reinterpret_cast<double *>(f->mem + kHdr + part);
     a.math_tab = c->math_tab;
+    a.trace = nullptr;
+#ifdef SMCB_TRACE
+    if (!g_trace_buf) {
+        SMCB_CUDA(cudaMalloc(&g_trace_buf, sizeof(unsigned long long) * (8 * 256 + 32 * 256 + 64 * 256)));
+        SMCB_CUDA(cudaMemset(g_trace_buf, 0, sizeof(unsigned long long) * (8 * 256 + 32 * 256 + 64 * 256)));
+    }
+    a.trace = g_trace_buf;
+#endif
     a.X[0] = d->X[0]; a.X[1] = d->X[1]; a.lw[0] = d->lw[0]; a.lw[1] = d->lw[1];
     a.A = reinterpret_cast<long long *>(d->A);
     a.cdf = d->cdf;
@@ -344,7 +355,8 @@ extern "C" int smcb_p2p_free(void *dev_ptr) {
 // debug builds only (profiles/build_variant.sh trace -DSMCB_TRACE): timeline of the last step-kernel launch
 extern "C" int smcb_debug_trace(unsigned long long *host_out, int n_words) {
     SMCB_CUDA(cudaDeviceSynchronize());
-    SMCB_CUDA(cudaMemcpyFromSymbol(host_out, smcb::g_trace, sizeof(unsigned long long) * (size_t)n_words));
+    if (!g_trace_buf) return SMCB_EINVAL;
+    SMCB_CUDA(cudaMemcpy(host_out, g_trace_buf, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost));
     return SMCB_OK;
 }
 #endif

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kCtlBlock) k_ctl_max(const double *__restrict_
 // ESS crosses alpha N (ESS is non-increasing in delta).  state = {lo, hi, max lw, done flag, result}.
 __global__ void __launch_bounds__(kCtlBlock) k_ctl_root_pass(const double *__restrict__ lw, int64_t n, double target,
                                                             double *state, double *partials, unsigned int *ticket,
-                                                            int final_pass) {
+                                                            int final_pass, double *raw_out) {
     __shared__ double s_red[kCtlBlock / 32][2 * kRootWays];
     __shared__ bool last;
     const double lo = state[0], hi = state[1], M = state[2];
@@ -494,6 +494,10 @@ __global__ void __launch_bounds__(kCtlBlock) k_ctl_root_pass(const double *__res
         tot[threadIdx.x] = v;
     }
     __syncthreads();
+    if (raw_out != nullptr) {                                      // sharded run: the caller sums these over the ranks
+        if (threadIdx.x < 2 * kRootWays) raw_out[threadIdx.x] = tot[threadIdx.x];
+        return;
+    }
     if (threadIdx.x == 0) {
         // f(delta) = ESS - target; f(lo) >= 0 by construction.  First j with f(delta_j) < 0 brackets the root.
         int jx = kRootWays;
@@ -520,11 +524,39 @@ __global__ void k_ctl_root_finish(const double *st, double epn, double *out) {
 
 // weighted mean and covariance of the rows of theta (rs.wmean_and_cov, resampling.py:341-358, as
 // ArrayRandomWalk.calibrate uses it), then L = scale * chol(cov): two passes, fixed-order block merges
-template <int PASS>
+__device__ __forceinline__ void chol_scaled(const double *cov, int d, double scale, double *L_out) {
+    // numpy.linalg.cholesky (smc_samplers.py:617-622), then the 2.38 / sqrt(d) scale; NaN if not positive definite
+    for (int j = 0; j < d; j++) {
+        double s = cov[j * d + j];
+        for (int k = 0; k < j; k++) s -= L_out[j * d + k] * L_out[j * d + k];
+        const double ljj = sqrt(s);
+        L_out[j * d + j] = ljj;
+        for (int i = j + 1; i < d; i++) {
+            double t = cov[i * d + j];
+            for (int k = 0; k < j; k++) t -= L_out[i * d + k] * L_out[j * d + k];
+            L_out[i * d + j] = t / ljj;
+        }
+        for (int i = 0; i < j; i++) L_out[i * d + j] = 0.0;
+    }
+    for (int i = 0; i < d * d; i++) L_out[i] *= scale;
+}
+
+// sharded runs: covariance from the (all-reduced) lower-triangular sums and the sum of weights, then the factor
+__global__ void k_ctl_chol(const double *tri, const double *sw, int d, double scale, double *work, double *L_out) {
+    if (threadIdx.x != 0) return;
+    for (int a_ = 0; a_ < d; a_++)
+        for (int b_ = 0; b_ <= a_; b_++) { const double c = tri[a_ * (a_ + 1) / 2 + b_] / sw[0]; work[a_ * d + b_] = c; work[b_ * d + a_] = c; }
+    chol_scaled(work, d, scale, L_out);
+}
+
+// FINAL: the last block turns the sums into the mean (pass 0) / the scaled Cholesky factor (pass 1); otherwise it
+// leaves the raw sums in `work` (pass 0: sum w x_j, sum w; pass 1: the lower triangle) for the caller to reduce
+// over ranks.  `mean` (pass 1) = the mean the deviations are taken from.
+template <int PASS, bool FINAL>
 __global__ void __launch_bounds__(kCtlBlock) k_ctl_wcov(const double *__restrict__ W, const double *__restrict__ theta,
                                                        int64_t n, int d, double *work /* [0..d) mean | d x d cov */,
                                                        double *partials, unsigned int *ticket, double scale,
-                                                       double *L_out) {
+                                                       double *L_out, const double *mean) {
     __shared__ bool last;
     extern __shared__ double s_acc[];                              // (kCtlBlock/32) x nvals
     const int nvals = (PASS == 0) ? d + 1 : d * (d + 1) / 2;
@@ -549,7 +581,7 @@ __global__ void __launch_bounds__(kCtlBlock) k_ctl_wcov(const double *__restrict
                     while ((a_ + 1) * (a_ + 2) / 2 <= v) a_++;
                     while (a_ * (a_ + 1) / 2 > v) a_--;
                     const int b_ = v - a_ * (a_ + 1) / 2;
-                    acc[k] += w * (row[a_] - work[a_]) * (row[b_] - work[b_]);
+                    acc[k] += w * (row[a_] - mean[a_]) * (row[b_] - mean[b_]);
                 }
             }
         }
@@ -578,27 +610,16 @@ __global__ void __launch_bounds__(kCtlBlock) k_ctl_wcov(const double *__restrict
         tot[v] = t;
     }
     __syncthreads();
-    if (PASS == 0) {
+    if (!FINAL) {
+        for (int v = threadIdx.x; v < nvals; v += kCtlBlock) work[v] = tot[v];
+    } else if (PASS == 0) {
         for (int j = threadIdx.x; j <= d; j += kCtlBlock) work[j] = (j < d) ? tot[j] / tot[d] : tot[d];     // mean | sum w
     } else if (threadIdx.x == 0) {
         const double sw = work[d];
         double *cov = work + d + 1;                                // d x d, symmetric
         for (int a_ = 0; a_ < d; a_++)
             for (int b_ = 0; b_ <= a_; b_++) { const double c = tot[a_ * (a_ + 1) / 2 + b_] / sw; cov[a_ * d + b_] = c; cov[b_ * d + a_] = c; }
-        // Cholesky (numpy.linalg.cholesky, distributions / smc_samplers.py:617-622), then the 2.38 / sqrt(d) scale
-        for (int j = 0; j < d; j++) {
-            double s = cov[j * d + j];
-            for (int k = 0; k < j; k++) s -= L_out[j * d + k] * L_out[j * d + k];
-            const double ljj = sqrt(s);                            // NaN if not positive definite, as LinAlgError would say
-            L_out[j * d + j] = ljj;
-            for (int i = j + 1; i < d; i++) {
-                double t = cov[i * d + j];
-                for (int k = 0; k < j; k++) t -= L_out[i * d + k] * L_out[j * d + k];
-                L_out[i * d + j] = t / ljj;
-            }
-            for (int i = 0; i < j; i++) L_out[i * d + j] = 0.0;
-        }
-        for (int i = 0; i < d * d; i++) L_out[i] *= scale;
+        chol_scaled(cov, d, scale, L_out);
     }
 }
 
@@ -617,7 +638,7 @@ extern "C" int smcb_next_annealing_epn(smcb_ctx *c, const double *lw, int64_t n,
     LAUNCHK(c, k_ctl_max, grid, kCtlBlock, 0, lw, n, partials, c->counters + 8, state + 2);
     for (int p = 0; p < kRootPasses; p++)
         LAUNCHK(c, k_ctl_root_pass, grid, kCtlBlock, 0, lw, n, alpha * (double)n, state, partials, c->counters + 9,
-                (p == kRootPasses - 1 ? 1 : 0) | (p == 0 ? 2 : 0));
+                (p == kRootPasses - 1 ? 1 : 0) | (p == 0 ? 2 : 0), (double *)nullptr);
     k_ctl_root_finish<<<1, 1, 0, c->stream>>>(state, epn, out_dev);     // result = epn + delta
     c->launches++;
     SMCB_CUDA(cudaGetLastError());
@@ -633,9 +654,49 @@ extern "C" int smcb_rw_calibrate(smcb_ctx *c, const double *W, const double *the
     double *partials = c->ws + 1024;
     const int grid = (int)((n + 7) / 8 < kCtlGrid ? (n + 7) / 8 : kCtlGrid);
     const int nv0 = d + 1, nv1 = d * (d + 1) / 2;
-    LAUNCHK(c, k_ctl_wcov<0>, grid, kCtlBlock, (kCtlBlock / 32) * (nv0 > 32 ? nv0 : 32) * sizeof(double), W, theta, n, d,
-            work, partials, c->counters + 10, scale, L_out);
-    LAUNCHK(c, k_ctl_wcov<1>, grid, kCtlBlock, (kCtlBlock / 32) * nv1 * sizeof(double), W, theta, n, d, work, partials,
-            c->counters + 11, scale, L_out);
+    LAUNCHK(c, (k_ctl_wcov<0, true>), grid, kCtlBlock, (kCtlBlock / 32) * (nv0 > 32 ? nv0 : 32) * sizeof(double), W, theta, n, d,
+            work, partials, c->counters + 10, scale, L_out, (const double *)nullptr);
+    LAUNCHK(c, (k_ctl_wcov<1, true>), grid, kCtlBlock, (kCtlBlock / 32) * nv1 * sizeof(double), W, theta, n, d, work, partials,
+            c->counters + 11, scale, L_out, (const double *)work);
+    return SMCB_OK;
+}
+
+// the same in pieces for a run sharded over ranks (the caller all-reduces between them):
+//   pass 0 (mean_dev == NULL): out_dev[0..d) = sum w x_j, out_dev[d] = sum w
+//   pass 1:                    out_dev[0..d(d+1)/2) = lower triangle of sum w (x - mean)(x - mean)^T
+extern "C" int smcb_wcov_sums(smcb_ctx *c, const double *W, const double *theta, int64_t n, int d, const double *mean_dev,
+                              double *out_dev) {
+    SMCB_REQUIRE(c && W && theta && out_dev && n >= 1 && d >= 1 && d <= 20, "smcb_wcov_sums: bad argument");
+    double *partials = c->ws + 1024;
+    const int grid = (int)((n + 7) / 8 < kCtlGrid ? (n + 7) / 8 : kCtlGrid);
+    const int nv0 = d + 1, nv1 = d * (d + 1) / 2;
+    if (mean_dev == nullptr)
+        LAUNCHK(c, (k_ctl_wcov<0, false>), grid, kCtlBlock, (kCtlBlock / 32) * (nv0 > 32 ? nv0 : 32) * sizeof(double), W, theta,
+                n, d, out_dev, partials, c->counters + 10, 1.0, (double *)nullptr, (const double *)nullptr);
+    else
+        LAUNCHK(c, (k_ctl_wcov<1, false>), grid, kCtlBlock, (kCtlBlock / 32) * nv1 * sizeof(double), W, theta, n, d, out_dev,
+                partials, c->counters + 11, 1.0, (double *)nullptr, mean_dev);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_chol_from_sums(smcb_ctx *c, const double *tri_dev, const double *sw_dev, int d, double scale,
+                                   double *L_out) {
+    SMCB_REQUIRE(c && tri_dev && sw_dev && L_out && d >= 1 && d <= 20, "smcb_chol_from_sums: bad argument");
+    LAUNCHK(c, k_ctl_chol, 1, 32, 0, tri_dev, sw_dev, d, scale, c->ws, L_out);
+    return SMCB_OK;
+}
+
+// one pass of the root-find's ESS grid without the bracket update (sharded runs): out32_dev = {s_j, q_j} for the 16
+// exponents lo + (hi - lo)(j + 1)/16, relative to the shift max_dev[0] (the GLOBAL maximum of lw)
+extern "C" int smcb_essl_grid(smcb_ctx *c, const double *lw, int64_t n, double lo, double hi, const double *max_dev,
+                              double *out32_dev) {
+    SMCB_REQUIRE(c && lw && max_dev && out32_dev && n >= 1, "smcb_essl_grid: bad argument");
+    double *state = c->ws;
+    double *partials = c->ws + 64;
+    const double init[5] = {lo, hi, 0.0, 0.0, 0.0};
+    SMCB_CUDA(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    SMCB_CUDA(cudaMemcpyAsync(state + 2, max_dev, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    const int grid = (int)((n + kCtlBlock - 1) / kCtlBlock < kCtlGrid ? (n + kCtlBlock - 1) / kCtlBlock : kCtlGrid);
+    LAUNCHK(c, k_ctl_root_pass, grid, kCtlBlock, 0, lw, n, 0.0, state, partials, c->counters + 9, 0, out32_dev);
     return SMCB_OK;
 }

@@ -46,6 +46,12 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 #ifndef SMCB_KU
 #define SMCB_KU 2                // pairs of particles in flight per thread in the streaming branch (1-D states)
 #endif
+#ifndef SMCB_SCAN_GROUPS
+#define SMCB_SCAN_GROUPS 4       // warps per pipeline group of the resampling scan (0: the whole CTA scans one tile)
+#endif
+#ifndef SMCB_RS_KR
+#define SMCB_RS_KR 2             // resampling move pass: pairs in flight per thread
+#endif
 #ifndef SMCB_L2PREF
 #define SMCB_L2PREF 0            // streaming branch: iterations ahead whose input lines are prefetched into L2 (0: off)
 #endif
@@ -95,6 +101,7 @@ struct FilterArgs {
     unsigned long long *bar; // grid-barrier arrivals, never reset
     double *blk_agg;         // multinomial: per-CTA sums of the exponential spacings (grid + 1)
     const double *math_tab;  // smcb_tables.h, built at context creation
+    unsigned long long *trace;   // SMCB_TRACE builds: per-CTA timeline of the last launch (else NULL, unused)
     int slab_it;             // iterations per slab of the streaming branch (host: chosen so the records fit)
     int slab_small;          // trailing iterations of a CTA's range handed out as single-iteration slabs
     int slab_lane;           // 1: a slab record holds the 32 lanes' own (m, s, q) (96 doubles); 0: their warp reduction
@@ -121,7 +128,6 @@ struct FilterArgs {
 #ifdef SMCB_TRACE
 // per-CTA timeline of the LAST launch of the step kernel: {start, dependency resolved, prologue done, main loop
 // done, exit, smid} in ns (8 words per CTA), then per warp the time its main loop ended
-__device__ unsigned long long g_trace[8 * 256 + 32 * 256];
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -132,8 +138,8 @@ __device__ __forceinline__ unsigned int smid() {
     asm volatile("mov.u32 %0, %smid;" : "=r"(r));
     return r;
 }
-#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) g_trace[8 * blockIdx.x + (slot)] = gtimer(); } while (0)
-#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) g_trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
+#define SMCB_TRACE_MARK(slot) do { if (threadIdx.x == 0) a.trace[8 * blockIdx.x + (slot)] = gtimer(); } while (0)
+#define SMCB_TRACE_WARP() do { if ((threadIdx.x & 31) == 0) a.trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer(); } while (0)
 #else
 #define SMCB_TRACE_MARK(slot) do { } while (0)
 #define SMCB_TRACE_WARP() do { } while (0)
@@ -295,6 +301,14 @@ struct StepSmem {
     int next;                 // next slab / iteration of the streaming branch
     int qn;                   // heavy entries queued by the scatter of a scan tile
     long long q[64][3];
+    // pipelined scan (scan_scatter_groups): prefix ring, per-group warp totals / prefixes / heavy-entry queues
+    double ringP[32];
+    int ringF[32];
+    double gwarp[8][8];
+    double gpref[8][2];
+    int gqn[8];
+    long long gq[8][8][3];
+    int *timeout_ptr;
     double peer[8][kMailStride];
     double goff[9], gpi[8];
     double pref[2];
@@ -872,7 +886,7 @@ constexpr int kHeavyQ = 64;
 template <int BS, class LOAD>
 __device__ __forceinline__ void scan_scatter_range(const LOAD &load, int64_t e0, int64_t e1, double p_b, double p_next,
                                                    double *out, double *s_warp, const Scatter &sc, bool last_cta,
-                                                   StepSmem &sh) {
+                                                   StepSmem &sh, int *s_hint, int hint_cap) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kTile = BS * kScanItems;
     double carry = 0.0;
@@ -915,31 +929,185 @@ __device__ __forceinline__ void scan_scatter_range(const LOAD &load, int64_t e0,
             for (int j = 0; j < kScanItems; j++)
                 if (i0 + j < e1) out[i0 + j] = o[j];
         }
-        // ---- scatter: this thread's 8 entries cover the outputs [F(tb), F(end)), `end` being the next thread's tb.
-        // ONE hint per output -- the first of the 8 entries; the move pass finds the entry inside the block with 8
-        // comparisons -- so the scan pays two F() and one store loop per thread instead of eight.
+        // ---- scatter.  The tile's entries cover the outputs [K0, K1) = [F(b_i), F(b_next)) (the same fp64 expressions
+        // the neighbouring tiles / CTAs use, so coverage is gap-free).  Normally that range fits the shared-memory hint
+        // buffer: every thread writes the (tile-relative) entry index of each of its outputs there -- 4-byte stores with
+        // neighbouring lanes writing neighbouring words -- and the CTA then copies the buffer to A with fully coalesced
+        // 16-byte stores.  A range too long for the buffer (a few entries with very many offspring) is written directly.
+        const bool cta_tail = last_tile;                            // this tile ends the CTA's range
+        const long long K0 = (blockIdx.x == 0 && base0 == 0) ? 0 : sc.F(b_i);
+        const long long K1 = (cta_tail && last_cta) ? sc.n_out : sc.F(cta_tail ? p_next : b_next);
+        const bool staged = (K1 - K0) <= (long long)hint_cap;
         if (i0 < e1) {
             const bool tail_thread = (i0 + kScanItems >= e1);       // owns the last entry of the CTA's range
-            double endv = (tid == BS - 1 || tail_thread) ? b_next : b_i + incl;
-            if (last_tile && tail_thread) endv = p_next;
-            long long ks = (blockIdx.x == 0 && i0 == 0) ? 0 : sc.F(tb);      // output 0 belongs to the first entry
-            long long ke = (last_tile && tail_thread && last_cta) ? sc.n_out : sc.F(endv);
-            ke = ke < ks ? ks : ke;
-            if (ke - ks > kHeavy) {
-                const int q = atomicAdd(&sh.qn, 1);
-                if (q < kHeavyQ) { sh.q[q][0] = ks; sh.q[q][1] = ke; sh.q[q][2] = i0; ks = ke; }
+            long long ks = (tid == 0) ? K0 : sc.F(tb);              // tb of thread 0 is b_i
+            const long long kend = (tid == BS - 1 || tail_thread) ? K1 : sc.F(b_i + incl);
+            ks = ks < K0 ? K0 : (ks > K1 ? K1 : ks);
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++) {
+                if (i0 + j < e1) {
+                    const bool last_entry = (j == kScanItems - 1) || (i0 + j + 1 >= e1);
+                    long long ke = last_entry ? kend : sc.F(o[j]);
+                    ke = ke < ks ? ks : (ke > kend ? kend : ke);
+                    if (staged) {
+                        const int rel = tid * kScanItems + j;
+                        for (long long k = ks; k < ke; k++) s_hint[(int)(k - K0)] = rel;
+                    } else {
+                        if (ke - ks > kHeavy) {
+                            const int q = atomicAdd(&sh.qn, 1);
+                            if (q < kHeavyQ) { sh.q[q][0] = ks; sh.q[q][1] = ke; sh.q[q][2] = i0 + j; ks = ke; }
+                        }
+                        for (long long k = ks; k < ke; k++) sc.A[k] = i0 + j;
+                    }
+                    ks = ke;
+                }
             }
-            for (long long k = ks; k < ke; k++) sc.A[k] = i0;
         }
         carry = carry_next;
         __syncthreads();
-        const int nq = sh.qn < kHeavyQ ? sh.qn : kHeavyQ;         // heavy entries: all threads fill their offspring
-        for (int q = 0; q < nq; q++) {
-            const long long ks = sh.q[q][0], ke = sh.q[q][1], jj = sh.q[q][2];
-            for (long long k = ks + tid; k < ke; k += BS) sc.A[k] = jj;
+        if (staged) {                                               // shared memory -> A, coalesced
+            const int cnt = (int)(K1 - K0);
+            for (int k = tid; k < cnt; k += BS) sc.A[K0 + k] = base0 + s_hint[k];
+        } else {
+            const int nq = sh.qn < kHeavyQ ? sh.qn : kHeavyQ;       // heavy entries: all threads fill their offspring
+            for (int q = 0; q < nq; q++) {
+                const long long ks = sh.q[q][0], ke = sh.q[q][1], jj = sh.q[q][2];
+                for (long long k = ks + tid; k < ke; k += BS) sc.A[k] = jj;
+            }
         }
-        if (nq > 0) __syncthreads();
+        __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------
+// The same scan + scatter as a PIPELINE of warp groups.  One CTA per SM means one block barrier domain per SM: with
+// the whole CTA on one tile every phase of the tile (loads, exponentials, warp scans, the prefix hand-over, stores)
+// is exposed -- measured 115 us for 16 B/particle where the three independent 256-thread CTAs of round 1 took 52.  So
+// the CTA's warps are split into NG groups of GW warps; group g takes the tiles g, g + NG, ... of the CTA's range, its
+// own named barrier (bar.sync g + 1) and its own slice of the hint buffer; the only thing a tile needs from its
+// predecessor is the running prefix P_t, handed over through a small shared-memory ring (value + epoch flag) right
+// after the group's warp scan -- a decoupled look-back of depth one with a FIXED association order
+// (P_{t+1} = min(P_t + total_t, p_next)), so the CDF is deterministic and monotone by construction as before.
+// ---------------------------------------------------------------------------
+constexpr int kScanRing = 32;
+constexpr int kGroupQ = 8;
+__device__ __forceinline__ int *sc_timeout(StepSmem &sh) { return sh.timeout_ptr; }
+
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BS, int GW, class LOAD>
+__device__ __forceinline__ void scan_scatter_groups(const LOAD &load, int64_t e0, int64_t e1, double p_b, double p_next,
+                                                    double *out, const Scatter &sc, bool last_cta, StepSmem &sh,
+                                                    int *s_hint_all, int hint_cap_total) {
+    constexpr int NG = BS / 32 / GW, GT = GW * 32, kTile = GT * kScanItems;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / GW, gw = warp % GW, gt = tid - grp * GT;
+    int *s_hint = s_hint_all + grp * (hint_cap_total / NG);
+    const int hint_cap = hint_cap_total / NG;
+    volatile double *ringP = sh.ringP;
+    volatile int *ringF = sh.ringF;
+    if (tid < kScanRing) { sh.ringF[tid] = (tid == 0) ? 1 : 0; if (tid == 0) sh.ringP[0] = p_b; }
+    if (tid < NG) sh.gqn[tid] = 0;
+    __syncthreads();
+    const int64_t nt = (e1 - e0 + kTile - 1) / kTile;
+    typename LOAD::Raw nxt;
+    if (grp < nt) load.fetch(e0 + (int64_t)grp * kTile + (int64_t)gt * kScanItems, e1, nxt);
+    for (int64_t t = grp; t < nt; t += NG) {
+        const int64_t base0 = e0 + t * kTile;
+        const int64_t i0 = base0 + (int64_t)gt * kScanItems;
+        const bool last_tile = (t == nt - 1);
+        double r[kScanItems];
+        const typename LOAD::Raw cur = nxt;
+        if (t + NG < nt) load.fetch(i0 + (int64_t)NG * kTile, e1, nxt);
+        load.weights(cur, i0, e1, r);
+#pragma unroll
+        for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
+        const double iw = warp_scan_monotone(r[kScanItems - 1], lane);
+        if (lane == 31) sh.gwarp[grp][gw] = iw;
+        group_sync(grp + 1, GT);
+        double woff = 0.0, total = 0.0;
+#pragma unroll
+        for (int w = 0; w < GW; w++) {
+            if (w < gw) woff = woff + sh.gwarp[grp][w];
+            total = total + sh.gwarp[grp][w];
+        }
+        if (gt == 0) {                                             // take P_t, hand P_{t+1} to the next tile at once
+            const int slot = (int)(t % kScanRing), nslot = (int)((t + 1) % kScanRing);
+            const long long t0 = clock64();
+            while (ringF[slot] != (int)(t + 1)) {
+                if (clock64() - t0 > 4000000000ll) { *sc_timeout(sh) = 3; break; }
+            }
+            const double Pt = ringP[slot];
+            const double Pn = fmin(Pt + total, p_next);
+            ringP[nslot] = Pn;
+            __threadfence_block();
+            ringF[nslot] = (int)(t + 2);
+            sh.gpref[grp][0] = Pt;
+            sh.gpref[grp][1] = Pn;
+        }
+        group_sync(grp + 1, GT);
+        const double b_i = sh.gpref[grp][0], b_next = sh.gpref[grp][1];
+        const double incl = woff + iw;
+        const double up = __shfl_up_sync(0xffffffffu, iw, 1);
+        const double excl = (lane == 0) ? woff : (woff + up);
+        const double tb = b_i + excl;
+        const double cap = fmin(b_i + incl, b_next);
+        double o[kScanItems];
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) o[j] = fmin(tb + r[j], cap);
+        if (i0 + kScanItems <= e1) {
+            store_items(out, i0, o);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++)
+                if (i0 + j < e1) out[i0 + j] = o[j];
+        }
+        // scatter (see scan_scatter_range): [K0, K1) = [F(P_t), F(P_{t+1})), staged in the group's hint buffer
+        const long long K0 = (blockIdx.x == 0 && t == 0) ? 0 : sc.F(b_i);
+        const long long K1 = (last_tile && last_cta) ? sc.n_out : sc.F(last_tile ? p_next : b_next);
+        const bool staged = (K1 - K0) <= (long long)hint_cap;
+        if (i0 < e1) {
+            const bool tail_thread = (i0 + kScanItems >= e1);
+            long long ks = (gt == 0) ? K0 : sc.F(tb);
+            const long long kend = (gt == GT - 1 || tail_thread) ? K1 : sc.F(b_i + incl);
+            ks = ks < K0 ? K0 : (ks > K1 ? K1 : ks);
+#pragma unroll
+            for (int j = 0; j < kScanItems; j++) {
+                if (i0 + j < e1) {
+                    const bool last_entry = (j == kScanItems - 1) || (i0 + j + 1 >= e1);
+                    long long ke = last_entry ? kend : sc.F(o[j]);
+                    ke = ke < ks ? ks : (ke > kend ? kend : ke);
+                    if (staged) {
+                        const int rel = gt * kScanItems + j;
+                        for (long long k = ks; k < ke; k++) s_hint[(int)(k - K0)] = rel;
+                    } else {
+                        if (ke - ks > kHeavy) {
+                            const int q = atomicAdd(&sh.gqn[grp], 1);
+                            if (q < kGroupQ) { sh.gq[grp][q][0] = ks; sh.gq[grp][q][1] = ke; sh.gq[grp][q][2] = i0 + j; ks = ke; }
+                        }
+                        for (long long k = ks; k < ke; k++) sc.A[k] = i0 + j;
+                    }
+                    ks = ke;
+                }
+            }
+        }
+        group_sync(grp + 1, GT);
+        if (staged) {
+            const int cnt = (int)(K1 - K0);
+            for (int k = gt; k < cnt; k += GT) sc.A[K0 + k] = base0 + s_hint[k];
+        } else {
+            const int nq = sh.gqn[grp] < kGroupQ ? sh.gqn[grp] : kGroupQ;
+            for (int q = 0; q < nq; q++) {
+                const long long ks = sh.gq[grp][q][0], ke = sh.gq[grp][q][1], jj = sh.gq[grp][q][2];
+                for (long long k = ks + gt; k < ke; k += GT) sc.A[k] = jj;
+            }
+        }
+        group_sync(grp + 1, GT);
+        if (gt == 0) sh.gqn[grp] = 0;
+    }
+    __syncthreads();
 }
 
 // multinomial: exponential spacings z = cumsum(-log u), n + 1 of them (resampling.py:536-537), blocked like
@@ -1029,7 +1197,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     __shared__ long long s_hi;
     __shared__ double s_warp[BS / 32];
 #ifdef SMCB_TRACE
-    if (threadIdx.x == 0) { g_trace[8 * blockIdx.x] = gtimer(); g_trace[8 * blockIdx.x + 5] = smid(); }
+    if (threadIdx.x == 0) { a.trace[8 * blockIdx.x] = gtimer(); a.trace[8 * blockIdx.x + 5] = smid(); }
 #endif
     // the tables are constants: their copy may start before the previous kernel has retired
     if (threadIdx.x == 0) { mtab_issue(a.math_tab, &s_tabbar); sh.next = 0; }
@@ -1351,8 +1519,15 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             const int64_t e1 = 2 * pend < n ? 2 * pend : n;
             if (count_path) {
                 Scatter sc{a.A, (double)n, (SCHEME == SMCB_RS_SYSTEMATIC) ? u_sys : 0.0, (long long)n};
+#if SMCB_SCAN_GROUPS
+                if (threadIdx.x == 0) sh.timeout_ptr = a.sync_timeout;
+                scan_scatter_groups<BS, SMCB_SCAN_GROUPS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, sc,
+                                                          blockIdx.x == gridDim.x - 1, sh, reinterpret_cast<int *>(s_stage),
+                                                          4 * kStage);
+#else
                 scan_scatter_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp, sc,
-                                       blockIdx.x == gridDim.x - 1, sh);
+                                       blockIdx.x == gridDim.x - 1, sh, reinterpret_cast<int *>(s_stage), 4 * kStage);
+#endif
             } else {
                 scan_range<BS>(load, 2 * pstart, e1, dec.p_b, dec.p_next, a.cdf, s_warp);
             }
@@ -1447,10 +1622,19 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
                 }
                 return lo_;
             };
-            constexpr int kR = 2;                                   // pairs in flight per thread
+            constexpr int kR = SMCB_RS_KR;                          // pairs in flight per thread
+#ifdef SMCB_TRACE
+            unsigned dbg_n = 0; long long dbg_d = 0;
+#endif
+#ifdef SMCB_TRACE
+            unsigned long long dbg_t[3] = {0, 0, 0};
+#endif
             for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kR * BS) {
+#ifdef SMCB_TRACE
+                const unsigned long long dbg_t0 = gtimer();
+#endif
                 long long h[kR][2];
-                double su[kR][2], cm[kR][2];
+                double su[kR][2], cm[kR][2], c0[kR][2], c1[kR][2];
                 bool valid[kR], two[kR], moved[kR];
 #pragma unroll
                 for (int r = 0; r < kR; r++) {                      // hints (scattered by the scan), then su
@@ -1478,42 +1662,95 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
                         su[r][1] = (u1 + (double)(2 * p + 1)) / M_;
                     }
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {                    // the hint names a block of 8 entries: count inside it
+                    for (int q = 0; q < 2; q++) {                    // the two CDF entries that decide the hint
                         long long hh = h[r][q];
                         hh = hh < 0 ? 0 : (hh > n - 1 ? n - 1 : hh);
-                        hh &= ~1ll;                                  // (hints are even by construction: 16-byte loads)
+                        moved[r] = moved[r] || hh != h[r][q];
+                        h[r][q] = hh;
                         const bool on = q == 0 ? valid[r] : two[r];
-                        int cnt = 0;
-                        if (on) {
-#pragma unroll
-                            for (int m = 0; m < 8; m += 2) {
-                                double c_a = 2.0, c_b = 2.0;
-                                // (plain loads: this SM touches these lines for the first time in this launch, after the
-                                // grid barrier, so L1 cannot hold an older copy -- and neighbouring outputs reuse them)
-                                if (hh + m + 1 < n) { const double2 cc = *reinterpret_cast<const double2 *>(a.cdf + hh + m); c_a = cc.x; c_b = cc.y; }
-                                else if (hh + m < n) c_a = a.cdf[hh + m];
-                                cnt += (c_a < su[r][q]) + (c_b < su[r][q]);
-                            }
-                        }
-                        cm[r][q] = (on && hh > 0 && cnt == 0) ? __ldcg(a.cdf + hh - 1) : -1.0;
-                        h[r][q] = hh + cnt;
-                        // inside the block (0 < cnt < 8) the count IS searchsorted's answer; at its edges it must be checked
-                        const bool edge_lo = cnt == 0 && !(cm[r][q] < su[r][q]);
-                        const bool edge_hi = cnt == 8 || hh + cnt > n - 1;
-                        if (on && (edge_lo || edge_hi)) h[r][q] = settle(hh + (cnt == 8 ? 7 : cnt), su[r][q]);
+                        // (plain loads: this SM touches these lines for the first time in this launch, after the grid
+                        // barrier, so L1 cannot hold an older copy -- and neighbouring outputs reuse them)
+                        c0[r][q] = on ? a.cdf[hh] : 2.0;
+                        cm[r][q] = (on && hh > 0) ? a.cdf[hh - 1] : -1.0;
+                        // stratified: the hint answers k / N and su_k lies up to 1 / N further, so about half of the
+                        // outputs belong to the NEXT entry -- fetch it with the other two instead of walking
+                        if (SCHEME == SMCB_RS_STRATIFIED) c1[r][q] = (on && hh + 1 < n) ? a.cdf[hh + 1] : 2.0;
                     }
                 }
+#ifdef SMCB_TRACE
+                const unsigned long long dbg_t1 = gtimer() + (unsigned long long)(c0[0][0] > 3.0);    // (after the loads)
+#endif
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const bool on = q == 0 ? valid[r] : two[r];
+                        bool ok = (cm[r][q] < su[r][q]) && (su[r][q] <= c0[r][q] || h[r][q] == n - 1);
+                        if (SCHEME == SMCB_RS_STRATIFIED) {
+                            if (on && !ok && c0[r][q] < su[r][q] && (su[r][q] <= c1[r][q] || h[r][q] + 1 == n - 1)) {
+                                h[r][q] += 1; moved[r] = true; ok = true;
+                            }
+                        }
+                        if (on && !ok && c0[r][q] < su[r][q] && h[r][q] + 1 < n) {
+                            // the hint is too low: ONE round trip for the next kWin entries (independent loads, mostly
+                            // one line) instead of a chain of dependent ones; the search below only runs past them
+                            constexpr int kWin = 6;
+                            const long long b = h[r][q] + 1;
+                            double wv[kWin];
+#pragma unroll
+                            for (int i = 0; i < kWin; i++) wv[i] = (b + i < n) ? __ldcg(a.cdf + b + i) : 2.0;
+                            int cnt = 0;
+#pragma unroll
+                            for (int i = 0; i < kWin; i++) cnt += (wv[i] < su[r][q]) ? 1 : 0;   // monotone CDF: a prefix
+                            if (cnt < kWin) {
+                                long long hn = b + cnt;
+                                h[r][q] = hn > n - 1 ? n - 1 : hn;
+                                moved[r] = true; ok = true;
+                            }
+                        }
+                        if (on && !ok) {
+#ifdef SMCB_TRACE
+                            const long long h_was = h[r][q];
+#endif
+                            h[r][q] = settle(h[r][q], su[r][q]);
+                            moved[r] = true;
+#ifdef SMCB_TRACE
+                            dbg_n++;
+                            const long long dd = h[r][q] > h_was ? h[r][q] - h_was : h_was - h[r][q];
+                            dbg_d = dd > dbg_d ? (dd > 0x7fffffffll ? 0x7fffffffll : dd) : dbg_d;
+#endif
+                        }
+                    }
                     if (!two[r]) h[r][1] = h[r][0];
-                    moved[r] = true;                                 // the hint was a block index: always write the ancestor
                 }
+#ifdef SMCB_TRACE
+                const unsigned long long dbg_t2 = gtimer() + (unsigned long long)(h[0][0] < -5);
+#endif
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
                     const int64_t p = p0 + (int64_t)r * BS;
                     if (valid[r]) finish_pair(p, Xi, Xi, h[r][0], h[r][1], h[r][0], h[r][1], moved[r]);
                 }
+#ifdef SMCB_TRACE
+                const unsigned long long dbg_t3 = gtimer() + (unsigned long long)(acc.w.s < -1.0);
+                dbg_t[0] = max(dbg_t[0], dbg_t1 - dbg_t0); dbg_t[1] = max(dbg_t[1], dbg_t2 - dbg_t1); dbg_t[2] = max(dbg_t[2], dbg_t3 - dbg_t2);
+#endif
             }
+#ifdef SMCB_TRACE
+            {   // per warp: end of its move loop | (settle calls << 32 | largest hint error) of the resampling step
+                const unsigned cnt = __reduce_add_sync(0xffffffffu, dbg_n);
+                const unsigned far = __reduce_max_sync(0xffffffffu, (unsigned)dbg_d);
+                if ((threadIdx.x & 31) == 0) {
+                    a.trace[8 * 256 + 32 * blockIdx.x + (threadIdx.x >> 5)] = gtimer();
+                    a.trace[8 * 256 + 32 * blockIdx.x + 16 + (threadIdx.x >> 5)] = ((unsigned long long)cnt << 32) | far;
+                }
+                // longest single round of this warp, by part: hint + CDF loads | settle | gather + propagate + reweight
+                for (int i = 0; i < 3; i++) {
+                    const unsigned v = __reduce_max_sync(0xffffffffu, (unsigned)dbg_t[i]);
+                    if ((threadIdx.x & 31) == 0) a.trace[40 * 256 + 64 * blockIdx.x + 4 * (threadIdx.x >> 5) + i] = v;
+                }
+            }
+#endif
         } else if (!a.rs_global) {
             const double M_ = (double)n;
             const double zlast = (SCHEME == SMCB_RS_MULTINOMIAL) ? __ldcg(a.su + n) : 1.0;

@@ -12,14 +12,14 @@ from particles_b200 import _lib, state_space_models as ssm
 from particles_b200.core import _FusedEngine
 from bench import load_data
 
-K, n = 60, int(os.environ.get("TRACE_N", "10000000"))
+K, n = int(os.environ.get("TRACE_K", "60")), int(os.environ.get("TRACE_N", "10000000"))
 ESS = float(os.environ.get("TRACE_ESSRMIN", "0.5"))
 CFG = os.environ.get("TRACE_CONFIG", "c2")
 if CFG == "c2":
     y = load_data(K)
     fk = ssm.Bootstrap(ssm=ssm.StochVol(), data=[np.atleast_1d(v) for v in y])
     sp = dict(ssm.fused_spec(fk)); sp["data"] = y.reshape(-1, 1).copy()
-    eng = _FusedEngine(sp, n, "systematic", ESS, 2024)
+    eng = _FusedEngine(sp, n, os.environ.get("TRACE_SCHEME", "systematic"), ESS, 2024)
 else:
     from particles_b200 import kalman, device
     device.seed(12345)
@@ -33,15 +33,17 @@ else:
 eng.step(K)
 torch.cuda.synchronize()
 lib = C.CDLL(_lib.SO_PATH)
-NW = 8 * 256 + 32 * 256
+NW = 8 * 256 + 32 * 256 + 64 * 256
 buf = (C.c_ulonglong * NW)()
 lib.smcb_debug_trace(buf, NW)
 raw = np.array(buf[:], dtype=np.uint64).astype(np.int64)
 G = int((raw[:8 * 256].reshape(256, 8)[:, 0] > 0).sum())
 a = raw[:8 * 256].reshape(256, 8)[:G]
-w = raw[8 * 256:].reshape(256, 32)[:G]
+w = raw[8 * 256:40 * 256].reshape(256, 32)[:G]
+parts = raw[40 * 256:].reshape(256, 16, 4)[:G]
 t0 = a[:, 1].min()                                   # first CTA past the grid dependency
-nw = max(1, int((w[0] > 0).sum()))
+rs_last = bool(eng.summ.cpu().numpy()[K - 1, 2])
+nw = 16 if rs_last else max(1, int((w[0] > 0).sum()))
 names = ["start", "dep_resolved", "prologue_done", "loop_done", "exit"]
 rec = {"grid": G, "warps": nw, "smid": a[:, 5].tolist(), "rs_flag_last_step": float(eng.summ.cpu().numpy()[K - 1, 2])}
 for i, nm in enumerate(names):
@@ -62,5 +64,18 @@ else:
                                                 "table_wait_and_rest": int(np.median(a[:, 2] - a[:, 7]))}
 rec["summary"]["warp_done"] = [int(wd.min()), int(np.median(wd)), int(wd.max())]
 rec["summary"]["within_cta_warp_spread_p50"] = int(np.median(wd.max(axis=1) - wd.min(axis=1)))
+if rs_last:                      # words 16.. of a CTA's warp area: (settle calls << 32) | largest hint error, per warp
+    stat = w[:, 16:32]
+    calls, far = (stat >> 32).sum(axis=1), (stat & 0xffffffff).max(axis=1)
+    rec["settle_calls_per_cta"], rec["max_hint_error_per_cta"] = calls.tolist(), far.tolist()
+    slow = np.argsort(a[:, 3])[-4:]
+    rec["summary"]["settle"] = {"calls_total": int(calls.sum()), "calls_per_cta_p50_max": [int(np.median(calls)), int(calls.max())],
+                                "max_hint_error": int(far.max()),
+                                "slowest_ctas": [[int(c), int(a[c, 3] - a[c, 7]), int(calls[c]), int(far[c])] for c in slow]}
+if rs_last:
+    rec["round_parts_max_ns"] = parts[:, :, :3].tolist()
+    late = np.argwhere(wd > np.median(wd) + 20000)
+    rec["summary"]["late_warps"] = [[int(c), int(wi), int(wd[c, wi])] + parts[c, wi, :3].tolist() for c, wi in late[:12]]
+    rec["summary"]["round_parts_max_ns_p50"] = np.median(parts[:, :, :3].reshape(-1, 3), axis=0).tolist()
 print(json.dumps(rec["summary"]))
 json.dump(rec, open(sys.argv[1], "w"))

@@ -54,6 +54,7 @@ def main():
         raise AssertionError("multinomial + global resampling should raise")
     except NotImplementedError:
         pass
+    tempering_checks(rank, world)
     dist.barrier()
     ref = g["stat/sv_T1000_N100000/logLt"]            # reference runs at N = 1e5 (same total for world=2)
     mu, sd = ref.mean(), ref.std(ddof=1) * np.sqrt(100_000 / (n_local * world))
@@ -69,6 +70,31 @@ def main():
         print("SHARDED OK")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def tempering_checks(rank, world):
+    """Waste-free adaptive tempering sharded over the ranks (BASELINE config 5): same evidence as the reference's
+    runs of the same total size (golden_tempering.npz: N chains x P), identical exponents on every rank."""
+    from particles_b200 import smc_samplers as ssp
+    from particles_b200.sharded_samplers import ShardedAdaptiveTempering
+    gt = np.load(os.path.join(ROOT, "tests", "golden", "golden_tempering.npz"))
+    data = gt["stat/data"]
+    N, P = (int(v) for v in gt["stat/meta"])
+    ref_ll = gt["stat/logLt"]
+    mu, sd = ref_ll.mean(), ref_ll.std(ddof=1)
+    lls = []
+    for s in range(4):
+        sm = ShardedAdaptiveTempering(model=ssp.LogisticRegression(data=data, prior_scale=5.0), M_local=N // world,
+                                      len_chain=P, ESSrmin=0.5, seed=90 + s).run()
+        ex = torch.tensor(sm.exponents + [sm.logLt], dtype=torch.float64, device="cuda")
+        allx = [torch.empty_like(ex) for _ in range(world)]
+        dist.all_gather(allx, ex)
+        assert all(torch.equal(o, ex) for o in allx), "ranks disagree on the exponents / evidence"
+        assert sm.exponents[-1] == 1.0 and abs(len(sm.exponents) - 1 - int(np.median(gt["stat/nsteps"]))) <= 1
+        lls.append(sm.logLt)
+    if rank == 0:
+        print("sharded tempering logLt", lls, "reference", mu, "+-", sd)
+    assert abs(np.mean(lls) - mu) < 3 * sd * np.sqrt(1 / 4 + 1 / len(ref_ll)) + 1e-6, (lls, mu, sd)
 
 
 def global_mode_checks(cases, rank, world):

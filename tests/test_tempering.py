@@ -157,6 +157,31 @@ def test_adaptive_tempering_vs_reference_runs(gt):
 
 
 @gpu
+def test_sharded_sampler_world1_vs_reference_runs(gt):
+    """The sharded waste-free sampler (global resampling through the two-level CDF, device control plane) with a
+    single rank: log evidence / posterior mean against the reference's runs, same number of tempering steps."""
+    pytest.importorskip("torch")
+    from particles_b200 import smc_samplers as ssp
+    from particles_b200.sharded_samplers import ShardedAdaptiveTempering
+    data = gt["stat/data"]
+    N, P = (int(v) for v in gt["stat/meta"])
+    ref_ll, ref_mean = gt["stat/logLt"], gt["stat/post_mean"]
+    mu, sd = ref_ll.mean(), ref_ll.std(ddof=1)
+    lls, means = [], []
+    for s in range(6):
+        sm = ShardedAdaptiveTempering(model=ssp.LogisticRegression(data=data, prior_scale=5.0), M_local=N, len_chain=P,
+                                      ESSrmin=0.5, seed=70 + s).run()
+        assert sm.exponents[-1] == 1.0 and sm.X.N == N * P
+        assert abs(len(sm.exponents) - 1 - int(np.median(gt["stat/nsteps"]))) <= 1
+        lls.append(sm.logLt)
+        means.append(sm.posterior_mean())
+    lls, means = np.array(lls), np.array(means)
+    assert abs(lls.mean() - mu) < 3 * sd * np.sqrt(1 / 6 + 1 / len(ref_ll)) + 1e-6, (lls, mu, sd)
+    msd = ref_mean.std(axis=0, ddof=1)
+    assert np.all(np.abs(means.mean(0) - ref_mean.mean(0)) < 4 * msd * np.sqrt(1 / 6 + 1 / 12) + 1e-3)
+
+
+@gpu
 def test_fixed_tempering_and_standard_move():
     """Tempering with a fixed exponent ladder and the non-waste-free move runs and agrees with the
     adaptive waste-free estimate of the same evidence."""
