@@ -47,7 +47,10 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 #define SMCB_KU 2                // pairs of particles in flight per thread in the streaming branch (1-D states)
 #endif
 #ifndef SMCB_SCAN_GROUPS
-#define SMCB_SCAN_GROUPS 4       // warps per pipeline group of the resampling scan (0: the whole CTA scans one tile)
+#define SMCB_SCAN_GROUPS 2       // warps per pipeline group of the resampling scan (0: the whole CTA scans one tile)
+#endif
+#ifndef SMCB_SPECULATE
+#define SMCB_SPECULATE 1         // sharded filters: start the streaming pass before the peers' statistics arrive
 #endif
 #ifndef SMCB_RS_KR
 #define SMCB_RS_KR 2             // resampling move pass: pairs in flight per thread
@@ -304,14 +307,16 @@ struct StepSmem {
     // pipelined scan (scan_scatter_groups): prefix ring, per-group warp totals / prefixes / heavy-entry queues
     double ringP[32];
     int ringF[32];
-    double gwarp[8][8];
-    double gpref[8][2];
-    int gqn[8];
-    long long gq[8][8][3];
+    double gwarp[16][8];
+    double gpref[16][2];
+    int gqn[16];
+    long long gq[16][8][3];
     int *timeout_ptr;
     double peer[8][kMailStride];
     double goff[9], gpi[8];
     double pref[2];
+    double carry[20];         // prologue_begin -> prologue_end: the shard's statistics and S_{s-1} (not held in registers
+                              // across a speculative streaming pass)
 };
 
 // exp(m - M) with the table family (inside the step kernels)
@@ -541,12 +546,19 @@ struct StepDecision {
 
 // compute_summaries of step s = t - 1 (core.py:351-367) + time_to_resample of step t (core.py:181-183),
 // by every CTA; the `writer` CTA also records S_s, the summary row and the moments row.
-template <bool APF, int BS>
-__device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
-                                                      bool need_prefix) {
+// Two halves.  prologue_begin: this shard's statistics of step s from the partial rows, sent to the peers at once
+// (sharded filters), and the shard's OWN resampling test -- the prediction a sharded step kernel speculates on.
+// prologue_end: the peers' statistics (the only wait), the global scalars, the decision, the bookkeeping.
+struct PrologueCarry {
+    bool mom;
+};
+
+template <bool APF>
+__device__ __forceinline__ bool prologue_begin(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
+                                               PrologueCarry &pc) {
     const long long s = t - 1;
     const int tid = threadIdx.x;
-    const bool mom = writer && a.moments != nullptr;
+    pc.mom = writer && a.moments != nullptr;
     // S_{s-1}: requested first, needed last
     StepState prev;
     prev.logLt = 0.0; prev.log_mean_w = 0.0; prev.nrs = 0; prev.rs_next = 0;
@@ -556,22 +568,51 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
         prev.nrs = __ldcg(&pp->nrs); prev.rs_next = __ldcg(&pp->rs_next);
     }
     double loc[16];
-    shard_totals<APF>(a, s, mom, sh, loc);
+    shard_totals<APF>(a, s, pc.mom, sh, loc);
     SMCB_TRACE_MARK(6);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) sh.carry[i] = loc[i];
+        sh.carry[16] = prev.logLt; sh.carry[17] = prev.log_mean_w;
+        sh.carry[18] = __longlong_as_double(prev.nrs); sh.carry[19] = __longlong_as_double((long long)prev.rs_next);
+    }
+    if (a.world > 1 && a.mail_local != nullptr) {
+        // fused exchange over NVLink peer memory: CTA 0 stores this shard's statistics of step s into every
+        // peer's mailbox (one lane per peer), fences, raises the epoch
+        if (writer && tid < a.world) {
+            double *slot = a.mail_peer[tid] + ((size_t)(s & 1) * a.world + a.rank) * kMailStride;
+#pragma unroll
+            for (int i = 0; i < 16; i++) slot[i] = loc[i];
+            __threadfence_system();
+            *reinterpret_cast<volatile double *>(slot + kMailEpoch) = (double)(s + 1);
+        }
+    }
+    // the shard's own ESS test: with ~N / world particles per shard it agrees with the global one except within
+    // sampling noise of the threshold
+    const Lse3 xl{loc[4], loc[5], loc[6]};
+    double lm_l, ess_l;
+    weights_scalars(xl, (double)a.n, lm_l, ess_l);
+    return (s + 1 < a.T) && (ess_l < (double)a.n * a.essrmin);
+}
+
+template <bool APF, int BS>
+__device__ __forceinline__ StepDecision prologue_end(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
+                                                     bool need_prefix, const PrologueCarry &pc) {
+    const long long s = t - 1;
+    const int tid = threadIdx.x;
+    __syncthreads();                                   // (sh.carry, written by thread 0 in prologue_begin)
+    StepState prev;
+    double loc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) loc[i] = sh.carry[i];
+    prev.logLt = sh.carry[16]; prev.log_mean_w = sh.carry[17];
+    prev.nrs = __double_as_longlong(sh.carry[18]); prev.rs_next = (int)__double_as_longlong(sh.carry[19]);
     double glob[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) glob[j] = loc[j];
     if (a.world > 1) {
         if (a.mail_local != nullptr) {
-            // fused exchange over NVLink peer memory: CTA 0 stores this shard's statistics of step s into every
-            // peer's mailbox (one lane per peer), fences, raises the epoch; every CTA waits for `world` epochs
-            if (writer && tid < a.world) {
-                double *slot = a.mail_peer[tid] + ((size_t)(s & 1) * a.world + a.rank) * kMailStride;
-#pragma unroll
-                for (int i = 0; i < 16; i++) slot[i] = loc[i];
-                __threadfence_system();
-                *reinterpret_cast<volatile double *>(slot + kMailEpoch) = (double)(s + 1);
-            }
+            // every CTA waits for `world` epochs in its own mailbox
             const double *box = a.mail_local + (size_t)(s & 1) * a.world * kMailStride;
             if (tid < a.world) {
                 wait_epoch(box + (size_t)tid * kMailStride + kMailEpoch, (double)(s + 1), a.sync_timeout);
@@ -655,6 +696,14 @@ __device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long 
         cta_prefix<BS>(v, sh, d.p_b, d.p_next);
     }
     return d;
+}
+
+template <bool APF, int BS>
+__device__ __forceinline__ StepDecision step_prologue(const FilterArgs &a, long long t, StepSmem &sh, bool writer,
+                                                      bool need_prefix) {
+    PrologueCarry pc;
+    prologue_begin<APF>(a, t, sh, writer, pc);
+    return prologue_end<APF, BS>(a, t, sh, writer, need_prefix, pc);
 }
 
 // all CTAs of the (co-resident) grid have arrived; `target` = arrivals expected in total since the filter was made
@@ -1002,6 +1051,7 @@ __device__ __forceinline__ void scan_scatter_groups(const LOAD &load, int64_t e0
                                                     double *out, const Scatter &sc, bool last_cta, StepSmem &sh,
                                                     int *s_hint_all, int hint_cap_total) {
     constexpr int NG = BS / 32 / GW, GT = GW * 32, kTile = GT * kScanItems;
+    static_assert(NG <= 15 && NG <= kScanRing && GW <= 8, "scan_scatter_groups: one named barrier (ids 1..15) and one table row per group");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = warp / GW, gw = warp % GW, gt = tid - grp * GT;
     int *s_hint = s_hint_all + grp * (hint_cap_total / NG);
@@ -1206,12 +1256,25 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
     SMCB_TRACE_MARK(1);
-    const StepDecision dec = step_prologue<APF, BS>(a, t, sh, blockIdx.x == 0, true);
+    // Sharded filters with the mailbox exchange SPECULATE: a step whose shard-local ESS test says "no resampling"
+    // starts its streaming pass at once and collects the peers' statistics afterwards -- the exchange latency (peer's
+    // step end + NVLink store + fence + poll) leaves the critical path.  The pass writes only the other half of the
+    // ping-pong buffers, so a wrong guess (global test says "resample": only within sampling noise of the threshold)
+    // costs one discarded pass and nothing else.
+    PrologueCarry pc;
+    const bool pred_rs = prologue_begin<APF>(a, t, sh, blockIdx.x == 0, pc);
+    // (not with the exact global resampling: there the peers pull ancestors out of THIS rank's previous generation
+    // during their resampling step, and waiting for their end-of-step statistics is what keeps that buffer intact)
+    const bool speculate = SMCB_SPECULATE && a.world > 1 && a.mail_local != nullptr && !a.rs_global && !pred_rs;
+    StepDecision dec;
+    dec.rs = 0; dec.nrs_prev = 0; dec.reset_c = 0.0; dec.xm = 0.0; dec.xs = 1.0; dec.p_b = 0.0; dec.p_next = 0.0;
+    if (!speculate) dec = prologue_end<APF, BS>(a, t, sh, blockIdx.x == 0, true, pc);
+    else __syncthreads();
     mbar_wait(&s_tabbar, 0);                           // (the prologue's barriers made the init visible)
     SMCB_TRACE_MARK(2);
     const int cur = (int)((t - 1) & 1);                // step s writes buffers [s & 1]
-    const bool rs = dec.rs != 0;
-    const double reset_c = dec.reset_c;
+    const bool rs = dec.rs != 0;                       // (a speculative step enters the resampling branch from below)
+    double reset_c = dec.reset_c;
     const StepK k = step_consts(a, t);
     const StepK kprev = step_consts(a, t - 1);
     const double *__restrict__ Xi = a.X[cur];
@@ -1495,7 +1558,20 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
         }
 #endif
         SMCB_TRACE_WARP();
-    } else {
+        if (!speculate) goto step_done;
+        // now the peers' statistics: bookkeeping, and was the guess right?
+        __syncthreads();
+        dec = prologue_end<APF, BS>(a, t, sh, blockIdx.x == 0, true, pc);
+        if (!dec.rs) goto step_done;
+        // no: discard the pass, take the resampling branch
+        reset_c = dec.reset_c;
+        acc_init(acc);
+        aux = lse3_empty();
+        n_slab = 0;
+        if (threadIdx.x == 0) sh.next = 0;
+        __syncthreads();
+    }
+    {
         // A = resampling(scheme, aux.W, M=N); Xp = X[A]; reset_weights (core.py:329-333)
         constexpr int kBarriers = (SCHEME == SMCB_RS_MULTINOMIAL) ? 2 : 1;     // grid barriers per resampling step
         unsigned long long bar_target = (unsigned long long)gridDim.x * ((unsigned long long)dec.nrs_prev * kBarriers);
@@ -1966,6 +2042,7 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
             }
         }
     }
+step_done:
     SMCB_TRACE_MARK(3);
     write_partial<D, APF, BS>(a, t, acc, aux, mom, sh, s_stage, n_slab);
     SMCB_TRACE_MARK(4);
