@@ -36,7 +36,8 @@ N_PER_GPU = 10_000_000
 ESSRMIN = 0.5
 SCHEME = "systematic"
 HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-FP64_INST_PER_PAIR = 184       # fp64 warp-instructions of the streaming loop per pair of particles (ncu, profiles/)
+FP64_INST_PER_PAIR = 105       # fp64 instructions of the streaming step per pair of particles; superseded by the
+                               # committed ncu capture (profiles/*_ncu_summary.json: move.fp64_inst_per_pair) when present
 
 
 def load_data(K):
@@ -74,6 +75,18 @@ def hbm_peak():
         except Exception:
             pass
     return HBM_FALLBACK_GBS, "fallback"
+
+
+def ncu_fp64_per_pair():
+    """fp64 (DFMA/DMUL/DADD/DSETP) instructions per pair of particles of a non-resampling step, counted by ncu's
+    source page in the committed capture; the constant above if there is none."""
+    import glob
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            return float(json.load(open(fn))["move"]["fp64_inst_per_pair"]), os.path.basename(fn)
+        except Exception:
+            continue
+    return float(FP64_INST_PER_PAIR), "constant"
 
 
 def ncu_traffic():
@@ -406,12 +419,13 @@ def run_b200(args):
             o3 = (C.c_double * 3)()
             _lib.check(ctx.lib.smcb_measure_fp64_peak(ctx.handle, 0.0, o3))
             # fp64 work of the streaming step per pair of particles (SASS of the loop body)
-            flops = FP64_INST_PER_PAIR * 2.0 * (n / 2.0)
+            per_pair, per_pair_src = ncu_fp64_per_pair()
+            flops = per_pair * 2.0 * (n / 2.0)
             roof["secondary"] = {"bound": "fp64", "peak": o3[0], "unit": "TFLOP/s (DFMA = 2 flop), measured by "
                                  "smcb_measure_fp64_peak in this run",
                                  "achieved": flops / (step_us * 1e-6) / 1e12,
                                  "frac": flops / (step_us * 1e-6) / 1e12 / o3[0],
-                                 "fp64_instructions_per_pair": FP64_INST_PER_PAIR}
+                                 "fp64_instructions_per_pair": per_pair, "fp64_instructions_source": per_pair_src}
         except Exception as exc:               # noqa: BLE001  (an older library without the probe)
             roof["secondary"] = {"bound": "fp64", "error": str(exc)}
 

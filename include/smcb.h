@@ -52,6 +52,10 @@ int64_t smcb_launch_count(const smcb_ctx *ctx);
 /* Weights.__init__, resampling.py:217-226.  lw is modified in place (NaN -> -inf,
  * line 220).  W_out may be NULL.  stats_out[4] = {max lw, log_mean, ESS, sum w}. */
 int smcb_normalise(smcb_ctx *ctx, double *lw, int64_t n, double *W_out, double *stats_out);
+/* The second half alone, W = exp(lw - m) / s (resampling.py:223-225) with statistics the caller already holds
+ * (stats[0] = m, stats[3] = s: the layout above; the fused filter's device state; for a sharded filter the GLOBAL
+ * (m, s), so that W sums to one over all ranks). */
+int smcb_weights_from_stats(smcb_ctx *ctx, const double *lw, int64_t n, const double *stats, double *W_out);
 
 #define SMCB_LSE_SUM 0  /* log_sum_exp   resampling.py:247-270            */
 #define SMCB_LSE_MEAN 1 /* log_mean_exp  resampling.py:291-317 (W optional) */

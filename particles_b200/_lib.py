@@ -48,6 +48,7 @@ PROTOTYPES = {
     "smcb_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "smcb_launch_count": (C.c_int64, [C.c_void_p]),
     "smcb_normalise": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp]),
+    "smcb_weights_from_stats": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp]),
     "smcb_lse": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int64, c_dp]),
     "smcb_exp_and_normalise": (C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp]),
     "smcb_wmean_and_var": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int64, C.c_int, c_dp]),

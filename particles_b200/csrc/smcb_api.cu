@@ -111,12 +111,39 @@ __global__ void __launch_bounds__(kBlock) k_lse(double *v, const double *__restr
     Lse3 acc[1] = {lse3_empty()};
     double sw = 0.0;  // sum of W (weighted mean only)
     const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-        double x = v[i];
-        if (MODE == kModeNormalise) {
-            if (x != x) { x = -CUDART_INF; v[i] = x; }
-            lse3_add(acc[0], x);
-        } else if (MODE == kModeWeightedMean) {
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (MODE != kModeWeightedMean) {
+        // eight independent loads in flight per thread and ONE running-max update per batch of eight (one exp per
+        // value, branch-free polynomial exp): the scalar loop with a library exp and a rescale test per value ran
+        // at a quarter of the HBM rate
+        bool saw_nan = false;
+        for (; i + 7 * stride < n; i += 8 * stride) {
+            double x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) x[j] = v[i + j * stride];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (x[j] != x[j]) {
+                    x[j] = -CUDART_INF;
+                    if (MODE == kModeNormalise) v[i + j * stride] = x[j];      // resampling.py:220
+                    else saw_nan = true;                                       // NumPy: max() of a NaN array is NaN
+                }
+            }
+            lse3_add_batch_f<8>(acc[0], x);
+        }
+        for (; i < n; i += stride) {
+            double x[1] = {v[i]};
+            if (x[0] != x[0]) {
+                x[0] = -CUDART_INF;
+                if (MODE == kModeNormalise) v[i] = x[0];
+                else saw_nan = true;
+            }
+            lse3_add_batch_f<1>(acc[0], x);
+        }
+        if (saw_nan) acc[0].s = CUDART_NAN;
+    } else {
+        for (; i < n; i += stride) {
+            double x = v[i];
             // log_mean_exp(v, W): m + log( sum W e^{v-m} / sum W )  (resampling.py:312-317)
             double w = W[i];
             sw += w;
@@ -126,9 +153,6 @@ __global__ void __launch_bounds__(kBlock) k_lse(double *v, const double *__restr
             double e = exp(-fabs(d));
             if (d > 0.0) { acc[0].s = acc[0].s * e + w; acc[0].m = x; }
             else acc[0].s += w * e;
-        } else {
-            if (x != x) acc[0].s = CUDART_NAN;  // NumPy: max() of a NaN array is NaN
-            lse3_add(acc[0], x);
         }
     }
     if (MODE == kModeWeightedMean) {
@@ -179,9 +203,26 @@ __global__ void __launch_bounds__(kBlock) k_exp_normalise(const double *__restri
                                                          const double *__restrict__ stats,
                                                          double *__restrict__ W) {
     const double m = stats[0], s = stats[3];
+    const double r = 1.0 / s;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
-        W[i] = exp(lw[i] - m) / s;
+    int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    // w / s as q + fma(-q, s, w) * r with q = w * r: the correctly rounded quotient without the division sequence
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) x[j] = lw[i + j * stride];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double w = fexp(x[j] - m);
+            const double q = w * r;
+            W[i + j * stride] = (s == s && s > 0.0 && s < CUDART_INF) ? fma(fma(-q, s, w), r, q) : w / s;
+        }
+    }
+    for (; i < n; i += stride) {
+        const double w = fexp(lw[i] - m);
+        const double q = w * r;
+        W[i] = (s == s && s > 0.0 && s < CUDART_INF) ? fma(fma(-q, s, w), r, q) : w / s;
+    }
 }
 
 extern "C" int smcb_normalise(smcb_ctx *c, double *lw, int64_t n, double *W_out,
@@ -191,6 +232,15 @@ extern "C" int smcb_normalise(smcb_ctx *c, double *lw, int64_t n, double *W_out,
     const int grid = grid_for(n, kBlock * 4);
     LAUNCH(c, k_lse<kModeNormalise>, grid, kBlock, lw, nullptr, n, c->ws, c->counters + 0, stats_out);
     if (W_out) LAUNCH(c, k_exp_normalise, grid_for(n, kBlock * 4), kBlock, lw, n, stats_out, W_out);
+    return SMCB_OK;
+}
+
+// W = exp(lw - m) / s from statistics the caller already holds (stats = {m, ., ., s}: the layout smcb_normalise
+// writes; the fused filter's device state; for a sharded filter the GLOBAL (m, s), so that W sums to one over all ranks)
+extern "C" int smcb_weights_from_stats(smcb_ctx *c, const double *lw, int64_t n, const double *stats, double *W_out) {
+    SMCB_REQUIRE(c && lw && stats && W_out, "smcb_weights_from_stats: NULL argument");
+    SMCB_REQUIRE(n >= 1, "smcb_weights_from_stats: n must be >= 1");
+    LAUNCH(c, k_exp_normalise, grid_for(n, kBlock * 4), kBlock, lw, n, stats, W_out);
     return SMCB_OK;
 }
 
@@ -252,28 +302,57 @@ __global__ void __launch_bounds__(kBlock) k_wmoments(const double *__restrict__ 
                                                     double *partials, unsigned int *ticket,
                                                     double *out) {
     // partials layout: [block][3*d + 1]: sum W, then per component sum W x, sum W x^2
-    __shared__ double s_red[kBlock / 32];
+    __shared__ double s_red[9][kBlock / 32];
     __shared__ bool s_last;
     const int nv = 1 + 2 * d;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int q = 0; q < nv; q++) {
-        double acc = 0.0;
-        for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-            double w = W[i];
-            if (q == 0) acc += w;
-            else {
-                double xv = x[(size_t)((q - 1) >> 1) * n + i];
-                acc += ((q - 1) & 1) ? w * (xv * xv) : w * xv;
+    // ONE pass over W and x per chunk of 4 components (d <= 4: one pass in all; the first version re-read W for every
+    // one of the 1 + 2 d sums), two elements in flight per thread
+    for (int c0 = 0; c0 < d; c0 += 4) {
+        const int dc = d - c0 < 4 ? d - c0 : 4;
+        double a[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) a[q] = 0.0;
+        int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+        for (; i + stride < n; i += 2 * stride) {
+            const double w0 = W[i], w1 = W[i + stride];
+            double x0[4], x1[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                x0[c] = (c < dc) ? x[(size_t)(c0 + c) * n + i] : 0.0;
+                x1[c] = (c < dc) ? x[(size_t)(c0 + c) * n + i + stride] : 0.0;
+            }
+            a[0] += w0;
+            a[0] += w1;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                a[1 + 2 * c] += w0 * x0[c]; a[2 + 2 * c] += w0 * (x0[c] * x0[c]);
+                a[1 + 2 * c] += w1 * x1[c]; a[2 + 2 * c] += w1 * (x1[c] * x1[c]);
+            }
+        }
+        for (; i < n; i += stride) {
+            const double w0 = W[i];
+            a[0] += w0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double xv = (c < dc) ? x[(size_t)(c0 + c) * n + i] : 0.0;
+                a[1 + 2 * c] += w0 * xv; a[2 + 2 * c] += w0 * (xv * xv);
             }
         }
 #pragma unroll
-        for (int mask = 16; mask > 0; mask >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, mask);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+        for (int q = 0; q < 9; q++) {
+            double acc = a[q];
+#pragma unroll
+            for (int mask = 16; mask > 0; mask >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, mask);
+            if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = acc;
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 9) {
+            const int q = threadIdx.x;
             double t = 0.0;
-            for (int w = 0; w < kBlock / 32; w++) t += s_red[w];
-            partials[(size_t)blockIdx.x * nv + q] = t;
+            for (int w = 0; w < kBlock / 32; w++) t += s_red[q][w];
+            const int slot = (q == 0) ? 0 : 2 * c0 + q;                 // sum W | per component sum W x, sum W x^2
+            if ((q == 0 && c0 == 0) || (q > 0 && (q - 1) / 2 < dc)) partials[(size_t)blockIdx.x * nv + slot] = t;
         }
         __syncthreads();
     }
@@ -376,14 +455,38 @@ static int scan_state(smcb_ctx *c, int64_t n, ScanState *st, int slot) {
 }
 
 template <typename T, typename LOAD>
-static int run_scan(smcb_ctx *c, const LOAD &load, int64_t n, T *out) {
+__global__ void __launch_bounds__(kBlock) k_scan_sums(LOAD load, int64_t n, int tiles_per_chunk, T *chunk_sum) {
+    scan_chunk_sums<T, LOAD>(load, n, tiles_per_chunk, chunk_sum);
+}
+template <typename T, typename LOAD>
+__global__ void __launch_bounds__(kBlock) k_scan_chunks(LOAD load, int64_t n, int tiles_per_chunk, const T *chunk_sum,
+                                                       int nchunks, T *out) {
+    scan_chunks<T, LOAD>(load, n, tiles_per_chunk, chunk_sum, nchunks, out);
+}
+
+// reduce-then-scan (smcb_scan.cuh); `slot` 0 / 1: two scans may be in flight on the stream (multinomial, residual).
+// SMCB_SCAN_LOOKBACK=1 in the environment selects the single-pass look-back kernel instead.
+template <typename T, typename LOAD>
+static int run_scan(smcb_ctx *c, const LOAD &load, int64_t n, T *out, int slot = 0) {
+    static const bool lookback = getenv("SMCB_SCAN_LOOKBACK") && atoi(getenv("SMCB_SCAN_LOOKBACK")) != 0;
     ScanState st;
-    int rc = scan_state(c, n, &st, 0);
+    int rc = scan_state(c, n, &st, slot);
     if (rc) return rc;
-    int64_t tiles = scan_tiles(n);
-    int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
-    k_scan<T, LOAD><<<grid, kBlock, 0, c->stream>>>(load, n, out, st);
-    c->launches++;
+    const int64_t tiles = scan_tiles(n);
+    if (lookback) {
+        int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
+        k_scan<T, LOAD><<<grid, kBlock, 0, c->stream>>>(load, n, out, st);
+        c->launches++;
+        SMCB_CUDA(cudaGetLastError());
+        return SMCB_OK;
+    }
+    const int64_t want = 148 * 6;                                  // chunks: a few CTAs per SM, <= kScanMaxChunks
+    const int tpc = (int)((tiles + want - 1) / want);
+    const int nchunks = (int)((tiles + tpc - 1) / tpc);
+    T *sums = reinterpret_cast<T *>(st.agg);                       // the slot's tile-state area doubles as the chunk sums
+    k_scan_sums<T, LOAD><<<nchunks, kBlock, 0, c->stream>>>(load, n, tpc, sums);
+    k_scan_chunks<T, LOAD><<<nchunks, kBlock, 0, c->stream>>>(load, n, tpc, sums, nchunks, out);
+    c->launches += 2;
     SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
 }
@@ -417,26 +520,56 @@ struct SuSpacings {    // resampling.py:537  z[:-1] / z[-1]
     __device__ __forceinline__ double operator()(int64_t k) const { return z[k] / z[M]; }
 };
 
+// Tile boundaries first, all at once: thread t finds where the first uniform of tile t lands (one global bisection
+// each, ~10^4 of them in parallel), so the tile kernel below knows its slice of the CDF without any block-wide
+// search; the slice is then staged in shared memory with coalesced loads and every output bisects THERE.  The first
+// version bracketed every tile with two block-cooperative searches of the whole CDF and bisected in global memory:
+// 174 us for 1e7 outputs.
+constexpr int kSearchStage = 4096;                  // CDF entries staged per tile (32 KB)
+
+template <typename SU>
+__global__ void __launch_bounds__(kBlock) k_search_bounds(const double *__restrict__ cdf, int64_t n, SU su, int64_t m,
+                                                         int64_t ntiles, int64_t *__restrict__ bnd) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t > ntiles) return;
+    const int64_t k = t < ntiles ? t * kSearchTile : m - 1;
+    bnd[t] = lower_bound(cdf, 0, n, su(k));
+}
+
 template <typename SU>
 __global__ void __launch_bounds__(kBlock) k_search(const double *__restrict__ cdf, int64_t n, SU su,
                                                   int64_t m, int64_t *__restrict__ A,
-                                                  int64_t a_offset) {
+                                                  int64_t a_offset, const int64_t *__restrict__ bnd) {
+    __shared__ double s_cdf[kSearchStage];
     const int64_t ntiles = (m + kSearchTile - 1) / kSearchTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t k0 = tile * kSearchTile;
-        const int64_t k1 = (k0 + kSearchTile < m ? k0 + kSearchTile : m) - 1;
-        // bracket the whole tile with two block-cooperative searches
-        const int64_t lo = block_lower_bound<kBlock>(cdf, 0, n, su(k0));
-        const int64_t hi = block_lower_bound<kBlock>(cdf, lo, n, su(k1));
+        // the uniforms are sorted, so the tile's answers lie in [lo, hi]
+        const int64_t lo = bnd[tile];
+        const int64_t hi = bnd[tile + 1];
         const int64_t hi1 = hi < n ? hi + 1 : n;
+        const int len = (hi1 - lo <= (int64_t)kSearchStage) ? (int)(hi1 - lo) : -1;
+        if (len >= 0) {
+            for (int i = threadIdx.x; i < len; i += kBlock) s_cdf[i] = cdf[lo + i];
+            __syncthreads();
+        }
 #pragma unroll
         for (int j = 0; j < kSearchPer; j++) {
             const int64_t k = k0 + (int64_t)j * kBlock + threadIdx.x;
             if (k < m) {
-                int64_t a = lower_bound(cdf, lo, hi1, su(k));
+                const double v = su(k);
+                int64_t a;
+                if (len >= 0) {
+                    int l = 0, h = len;
+                    while (l < h) { const int mid = (l + h) >> 1; if (s_cdf[mid] < v) l = mid + 1; else h = mid; }
+                    a = lo + l;
+                } else {
+                    a = lower_bound(cdf, lo, hi1, v);
+                }
                 A[a_offset + k] = a < n - 1 ? a : n - 1;
             }
         }
+        if (len >= 0) __syncthreads();
     }
 }
 
@@ -445,9 +578,17 @@ static int run_search(smcb_ctx *c, const double *cdf, int64_t n, const SU &su, i
                       int64_t *A, int64_t a_offset) {
     if (m <= 0) return SMCB_OK;
     int64_t tiles = (m + kSearchTile - 1) / kSearchTile;
+    // tile boundaries live in scan slot 0 of the workspace (the CDF's scan, stream-ordered before us, is done with it)
+    const size_t base = (kWsPartials + 16) * sizeof(double);
+    const size_t need = (size_t)(tiles + 2) * sizeof(int64_t);
+    const size_t sc = scan_state_bytes(n);
+    int rc = check_ws(c, base + 2 * (need > sc ? need : sc) + 64);
+    if (rc) return rc;
+    int64_t *bnd = reinterpret_cast<int64_t *>((char *)c->ws + base);
+    k_search_bounds<SU><<<(int)((tiles + 1 + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(cdf, n, su, m, tiles, bnd);
     int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
-    k_search<SU><<<grid, kBlock, 0, c->stream>>>(cdf, n, su, m, A, a_offset);
-    c->launches++;
+    k_search<SU><<<grid, kBlock, 0, c->stream>>>(cdf, n, su, m, A, a_offset, bnd);
+    c->launches += 2;
     SMCB_CUDA(cudaGetLastError());
     return SMCB_OK;
 }
@@ -656,15 +797,7 @@ extern "C" int smcb_resample(smcb_ctx *c, int scheme, const double *W, int64_t n
         if (scheme == SMCB_RS_SYSTEMATIC) return run_search(c, cdf, n, SuSystematic{u_in, (double)m}, m, A_out, 0);
         if (scheme == SMCB_RS_STRATIFIED) return run_search(c, cdf, n, SuStratified{u_in, (double)m}, m, A_out, 0);
         // multinomial: z = cumsum(-log u) over m+1 uniforms (second scan), su = z[:-1]/z[-1]
-        ScanState st;
-        if ((rc = scan_state(c, m + 1, &st, 1))) return rc;
-        {
-            int64_t tiles = scan_tiles(m + 1);
-            int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
-            k_scan<double, LoadNegLog><<<grid, kBlock, 0, c->stream>>>(LoadNegLog{u_in}, m + 1, z, st);
-            c->launches++;
-            SMCB_CUDA(cudaGetLastError());
-        }
+        if ((rc = run_scan<double>(c, LoadNegLog{u_in}, m + 1, z, 1))) return rc;
         return run_search(c, cdf, n, SuSpacings{z, m}, m, A_out, 0);
     }
     if (scheme == SMCB_RS_RESIDUAL) {
@@ -674,15 +807,7 @@ extern "C" int smcb_resample(smcb_ctx *c, int scheme, const double *W, int64_t n
         // residual weights res/sres -> cdf; spacings over (sres + 1) uniforms: only the first
         // sres + 1 entries of z are meaningful, and z[k]/z[sres] needs exactly those.
         if ((rc = run_scan<double>(c, LoadResidual{W, (double)m, cum_ip, n}, n, cdf))) return rc;
-        ScanState st;
-        if ((rc = scan_state(c, m + 1, &st, 1))) return rc;
-        {
-            int64_t tiles = scan_tiles(m + 1);
-            int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
-            k_scan<double, LoadNegLog><<<grid, kBlock, 0, c->stream>>>(LoadNegLog{u_in}, m + 1, z, st);
-            c->launches++;
-            SMCB_CUDA(cudaGetLastError());
-        }
+        if ((rc = run_scan<double>(c, LoadNegLog{u_in}, m + 1, z, 1))) return rc;
         LAUNCH(c, k_search_residual, grid_for(m, kBlock * 4), kBlock, cdf, n,
                SuSpacingsDyn{z, cum_ip, n, m}, A_out);
         return SMCB_OK;

@@ -330,4 +330,25 @@ __device__ __forceinline__ void lse3_add_batch(Lse3 &a, const double (&v)[NV]) {
     }
 }
 
+// the same with the polynomial family (stand-alone kernels: no shared-memory tables)
+template <int NV>
+__device__ __forceinline__ void lse3_add_batch_f(Lse3 &a, const double (&v)[NV]) {
+    double mb = v[0];
+#pragma unroll
+    for (int j = 1; j < NV; j++) mb = fmax(mb, v[j]);
+    if (mb > a.m) {
+        const double r = fexp_neg(a.m - mb);
+        a.s *= r;
+        a.q *= r * r;
+        a.m = mb;
+    }
+    if (a.m == -CUDART_INF) return;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const double e = fexp_neg(v[j] - a.m);
+        a.s += e;
+        a.q = fma(e, e, a.q);
+    }
+}
+
 }  // namespace smcb

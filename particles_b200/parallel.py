@@ -90,6 +90,20 @@ class ShardedSMC:
         return self._engine.X[(self.t - 1) & 1]
 
     @property
+    def W(self):
+        """This rank's slice of the GLOBALLY normalised weights (they sum to one over all ranks): exp(lw - m) / s with
+        the (max, sum exp) of all N_global particles that every rank holds after the last step."""
+        import torch
+        from .device import context, empty, ptr
+        st = self._engine.state()                     # [.., 4: ESS, 5: log_mean, 6: max, 7: sum exp] of ALL particles
+        lw = self._engine.lw[(self.t - 1) & 1]
+        stats = torch.tensor([st[6], st[5], st[4], st[7]], dtype=torch.float64, device=lw.device)
+        W = empty(lw.shape[0], like=lw)
+        ctx = context(lw.device)
+        _lib.check(ctx.lib.smcb_weights_from_stats(ctx.handle, ptr(lw), lw.shape[0], ptr(stats), ptr(W)))
+        return W
+
+    @property
     def A(self):
         """Ancestors of the last resampling step: shard-local indices ("island"), global particle
         indices ("global")."""

@@ -121,9 +121,10 @@ class Weights:
             if self._W is None:
                 ctx = context(self.lw.device)
                 W = torch.empty_like(self.lw)
-                # W = exp(lw - m) / s with the (m, s) of the normalise pass
-                _lib.check(ctx.lib.smcb_normalise(ctx.handle, ptr(self.lw), self.lw.shape[0],
-                                                  ptr(W), ptr(self._stats)))
+                # W = exp(lw - m) / s with the (m, s) already on the device (the normalise pass above, or the fused
+                # filter's own state -- never recomputed, so a sharded filter's global (m, s) stay global)
+                _lib.check(ctx.lib.smcb_weights_from_stats(ctx.handle, ptr(self.lw), self.lw.shape[0],
+                                                           ptr(self._stats), ptr(W)))
                 self._W = W
             return self._W
         raise AttributeError(name)

@@ -34,6 +34,31 @@ from .device import as_device, context, empty, ptr
 from .smc_samplers import LogisticRegression, ThetaParticles
 
 
+def plan_global_resample(mass, u, M, world, rank):
+    """Host plan of one global systematic resampling (resampling.py:606-610 on the concatenation of the shards) seen
+    from ``rank``: ``mass`` = the shards' shares of the total weight (identical on every rank), ``u`` the common
+    uniform, ``M`` chain slots per rank.  Returns (mine, v, send_counts, recv_counts): the global slots whose grid
+    point falls into this rank's share of the global CDF (consecutive), their positions ``v`` in this shard's OWN
+    normalised CDF, and the ``all_to_all_single`` split sizes (slot s lives on rank s // M)."""
+    mass = np.asarray(mass, dtype=np.float64)
+    Mg = world * M
+    goff = np.concatenate([[0.0], np.cumsum(mass)])
+    goff[-1] = max(goff[-1], 1.0)
+    su = (u + np.arange(Mg)) / Mg                                      # global grid, the same on every rank
+    owner = np.minimum(np.searchsorted(goff, su, side="right") - 1, world - 1)
+    for _ in range(world):                                             # a grid point on an empty shard's edge: step down
+        owner = np.where((mass[owner] > 0.0) | (owner == 0), owner, owner - 1)
+    for _ in range(world):                                             # (rank 0 itself empty: step up)
+        owner = np.where((mass[owner] > 0.0) | (owner == world - 1), owner, owner + 1)
+    mine = np.flatnonzero(owner == rank)
+    v = np.minimum((su[mine] - goff[rank]) / mass[rank], 1.0) if mine.size else np.zeros(0)
+    v = np.maximum(v, 0.0)
+    slot_rank = np.arange(Mg) // M
+    send_counts = [int(np.sum(slot_rank[mine] == r)) for r in range(world)]
+    recv_counts = [int(np.sum((owner == r) & (slot_rank == rank))) for r in range(world)]
+    return mine, v, send_counts, recv_counts
+
+
 class ShardedAdaptiveTempering:
     """``ShardedAdaptiveTempering(model, M_local, len_chain).run()`` on every rank of an NCCL group.
     ``M_local`` resampled starting points (chains) and ``M_local * len_chain`` particles per rank."""
@@ -107,26 +132,16 @@ class ShardedAdaptiveTempering:
         that owns each chain slot.  ``W_loc``: this shard's weights normalised to sum to 1, ``mass``: the shards'
         shares of the total (host array, identical on every rank), ``u``: the common uniform."""
         world, M, rank = self.world, self.M, self.rank
-        Mg = world * M
-        goff = np.concatenate([[0.0], np.cumsum(mass)])
-        goff[-1] = max(goff[-1], 1.0)
-        su = (u + np.arange(Mg)) / Mg                                  # global grid, the same on every rank
-        owner = np.minimum(np.searchsorted(goff, su, side="right") - 1, world - 1)
-        owner = np.where(mass[owner] > 0.0, owner, np.maximum(owner - 1, 0))
-        mine = np.flatnonzero(owner == rank)                           # consecutive slots
+        mine, v, send_counts, recv_counts = plan_global_resample(mass, u, M, world, rank)
         fields = ("theta", "lprior", "llik", "lpost")
         send = {}
         if mine.size:
-            v = np.minimum((su[mine] - goff[rank]) / mass[rank], 1.0)  # positions in this shard's own CDF
             A = rs.inverse_cdf(as_device(v), W_loc)                    # cumsum + searchsorted kernels
             sel = x[A]                                                 # gather kernels
             send = {k: getattr(sel, k) for k in fields}
         d = x.theta.shape[1]
         if world == 1:
             return ThetaParticles(shared=x.shared.copy(), **send)
-        # slot s lives on rank s // M: how many of my rows go to each rank, how many I get from each
-        send_counts = [int(np.sum((mine // M) == r)) for r in range(world)]
-        recv_counts = [int(np.sum((owner == r) & ((np.arange(Mg) // M) == rank))) for r in range(world)]
         out = {}
         for k in fields:
             w_ = d if k == "theta" else 1

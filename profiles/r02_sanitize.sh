@@ -4,6 +4,8 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
 cat > /tmp/san_mix.py <<'P'
+import os, sys
+sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import particles_b200 as pb
 from particles_b200 import state_space_models as ssm, kalman

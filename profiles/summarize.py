@@ -8,6 +8,7 @@ import shutil
 import sys
 
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+N_PARTICLES = float(sys.argv[2]) if len(sys.argv) > 2 else 1e7      # particles of the profiled run (bench.py: 1e7)
 SRC, DST = "gpurun_out", "profiles"
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
@@ -52,7 +53,7 @@ def mix(fn):
         op = m.group(2).split(".")[0] if m else "?"
         ops[op] = ops.get(op, 0) + e
         tot += e
-    return tot, dict(sorted(ops.items(), key=lambda kv: -kv[1])[:16])
+    return tot, dict(sorted(ops.items(), key=lambda kv: -kv[1])[:24])
 
 
 out = {}
@@ -74,6 +75,10 @@ for k, label in [("move", "step kernel, no-resampling step (config 2's common ca
     tot, ops = mix(f"{SRC}/{k}_{TAG}_source.csv")
     d["warp_instructions_executed"] = tot
     d["top_opcodes"] = ops
+    # thread-level instructions per PAIR of particles (the kernel's work unit): warp instructions / (N / 2 / 32)
+    pairs_warp = N_PARTICLES / 2 / 32
+    d["instructions_per_pair"] = tot / pairs_warp
+    d["fp64_inst_per_pair"] = sum(v for op, v in ops.items() if op in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")) / pairs_warp
     rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
     if rd and wr:
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}

@@ -55,6 +55,14 @@ def main():
     except NotImplementedError:
         pass
     tempering_checks(rank, world)
+    # the public wrapper: globally normalised weights (each rank holds its slice; the slices sum to one)
+    from particles_b200.parallel import ShardedSMC
+    fk60 = ssm.Bootstrap(ssm=ssm.StochVol(), data=fk.data[:60])
+    sm = ShardedSMC(fk=fk60, N=40_000, seed=5)
+    sm.run()
+    tot = sm.W.sum().reshape(1)
+    dist.all_reduce(tot)
+    assert abs(float(tot) - 1.0) < 1e-12 and float(sm.W.min()) >= 0.0, float(tot)
     dist.barrier()
     ref = g["stat/sv_T1000_N100000/logLt"]            # reference runs at N = 1e5 (same total for world=2)
     mu, sd = ref.mean(), ref.std(ddof=1) * np.sqrt(100_000 / (n_local * world))

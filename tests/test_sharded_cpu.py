@@ -177,3 +177,43 @@ def test_global_ancestors_skips_empty_shards():
     A = par.global_ancestors(su, goff, gpi, cdfs)
     W = np.concatenate([np.full(4, 0.125), np.zeros(4), np.full(4, 0.125)])
     assert np.array_equal(A, orc.systematic(W, 12, u=np.array([0.3])))
+
+
+def test_global_resampling_plan_of_the_sharded_sampler():
+    """Host plan of ShardedAdaptiveTempering's global systematic resampling: every chain slot is served by exactly
+    one rank, send / receive counts of the all_to_all are transposes of each other, and the two-level inverse CDF
+    picks the same ancestors as one searchsorted over the concatenated weights."""
+    import importlib.util
+    import sys
+    import types
+    # the module imports torch-backed helpers at import time; only the NumPy planner is exercised here
+    spec = importlib.util.find_spec("particles_b200.sharded_samplers")
+    src = open(spec.origin).read()
+    start, stop = src.index("def plan_global_resample"), src.index("class ShardedAdaptiveTempering")
+    ns = {"np": np}
+    exec(src[start:stop], ns)
+    plan = ns["plan_global_resample"]
+    rng = np.random.default_rng(5)
+    for world, M, n_loc in ((2, 50, 400), (3, 33, 257), (4, 16, 128)):
+        for trial in range(4):
+            w = [rng.random(n_loc) ** (3 + 4 * trial) for _ in range(world)]
+            if trial == 3:
+                w[1][:] = 0.0                                     # an empty shard
+            tot = sum(x.sum() for x in w)
+            mass = np.array([x.sum() / tot for x in w])
+            u = rng.random()
+            Mg = world * M
+            plans = [plan(mass, u, M, world, r) for r in range(world)]
+            served = np.concatenate([p[0] for p in plans])
+            assert np.array_equal(np.sort(served), np.arange(Mg))
+            S = np.array([p[2] for p in plans]); R = np.array([p[3] for p in plans])
+            assert np.array_equal(S, R.T) and S.sum() == Mg and np.all(R.sum(axis=1) == M)
+            # ancestors: two-level vs flat
+            flat = np.concatenate(w) / tot
+            ref = np.minimum(np.searchsorted(np.cumsum(flat), (u + np.arange(Mg)) / Mg, "left"), world * n_loc - 1)
+            got = np.empty(Mg, dtype=np.int64)
+            for r, (mine, v, _s, _r) in enumerate(plans):
+                if mine.size:
+                    cdf = np.cumsum(w[r] / w[r].sum())
+                    got[mine] = r * n_loc + np.minimum(np.searchsorted(cdf, v, "left"), n_loc - 1)
+            assert np.mean(got != ref) < 0.02 and np.max(np.abs(got - ref)) <= 2   # rounding of the two-level CDF only
