@@ -580,6 +580,23 @@ class BearingsOnly(SSM):
         return Normal(loc=angle, scale=self.sigmaY)
 
 
+class MVStochVol(SSM):
+    """particles/state_space_models.py:633-654 (mu, covX, corY, F have no defaults in the reference: pass them)."""
+    default_params = {"mu": 0.0, "covX": None, "corY": None, "F": None}
+
+    def offset(self):
+        return self.mu - np.dot(self.F, self.mu)
+
+    def PX0(self):
+        return MvNormal(loc=self.mu, cov=self.covX)
+
+    def PX(self, t, xp):
+        return MvNormal(loc=np.dot(xp, self.F.T) + self.offset(), cov=self.covX)
+
+    def PY(self, t, xp, x):
+        return MvNormal(scale=np.exp(0.5 * x), cov=self.corY)
+
+
 class MVLinearGauss(SSM):
     """particles/kalman.py:296-361."""
 

@@ -52,6 +52,9 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 #ifndef SMCB_SPECULATE
 #define SMCB_SPECULATE 1         // sharded filters: start the streaming pass before the peers' statistics arrive
 #endif
+#ifndef SMCB_RS_PIPE
+#define SMCB_RS_PIPE 1             // resampling move pass of the 1-D models: hints two rounds ahead, CDF entries one
+#endif
 #ifndef SMCB_RS_KR
 #define SMCB_RS_KR 2             // resampling move pass: pairs in flight per thread
 #endif
@@ -1705,26 +1708,58 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
 #ifdef SMCB_TRACE
             unsigned long long dbg_t[3] = {0, 0, 0};
 #endif
-            for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kR * BS) {
-#ifdef SMCB_TRACE
-                const unsigned long long dbg_t0 = gtimer();
-#endif
-                long long h[kR][2];
-                double su[kR][2], cm[kR][2], c0[kR][2], c1[kR][2];
-                bool valid[kR], two[kR], moved[kR];
-#pragma unroll
-                for (int r = 0; r < kR; r++) {                      // hints (scattered by the scan), then su
-                    moved[r] = false;
-                    const int64_t p = p0 + (int64_t)r * BS;
-                    valid[r] = p < pend;
-                    two[r] = valid[r] && (2 * p + 1 < n);
-                    h[r][0] = h[r][1] = 0;
-                    if (two[r]) { const longlong2 hh = __ldcg(reinterpret_cast<const longlong2 *>(a.A + 2 * p)); h[r][0] = hh.x; h[r][1] = hh.y; }
-                    else if (valid[r]) h[r][0] = __ldcg(a.A + 2 * p);
-                }
+            // one round = kR pairs per thread, in three parts: the hints (A, written by the scan), the CDF entries that
+            // verify them, and verify + repair + gather + propagate.  The first two are plain loads with no arithmetic
+            // behind them, so for the 1-D models they are issued one / two rounds AHEAD (software pipeline): the move
+            // pass is a chain hint -> CDF -> gather -> fp64 work, and with 16 warps per SM the chain's latencies were
+            // not covered by the other warps' arithmetic (move pass 132 us against 78 us for the same arithmetic alone).
+            struct Hints { long long h[kR][2]; };
+            struct Cdf { double c0[kR][2], cm[kR][2], c1[kR][(SCHEME == SMCB_RS_STRATIFIED) ? 2 : 1]; };
+            auto ld_hints = [&](int64_t p0, Hints &H) {
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
                     const int64_t p = p0 + (int64_t)r * BS;
+                    H.h[r][0] = H.h[r][1] = 0;
+                    if (p < pend && 2 * p + 1 < n) {
+                        const longlong2 hh = __ldcg(reinterpret_cast<const longlong2 *>(a.A + 2 * p));
+                        H.h[r][0] = hh.x; H.h[r][1] = hh.y;
+                    } else if (p < pend) {
+                        H.h[r][0] = __ldcg(a.A + 2 * p);
+                    }
+                }
+            };
+            auto ld_cdf = [&](int64_t p0, const Hints &H, Cdf &Cc) {
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int64_t p = p0 + (int64_t)r * BS;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {                    // the two CDF entries that decide the hint
+                        long long hh = H.h[r][q];
+                        hh = hh < 0 ? 0 : (hh > n - 1 ? n - 1 : hh);
+                        const bool on = (p < pend) && (q == 0 || 2 * p + 1 < n);
+                        // (plain loads: this SM touches these lines for the first time in this launch, after the grid
+                        // barrier, so L1 cannot hold an older copy -- and neighbouring outputs reuse them)
+                        Cc.c0[r][q] = on ? a.cdf[hh] : 2.0;
+                        Cc.cm[r][q] = (on && hh > 0) ? a.cdf[hh - 1] : -1.0;
+                        // stratified: the hint answers k / N and su_k lies up to 1 / N further, so about half of the
+                        // outputs belong to the NEXT entry -- fetch it with the other two instead of walking
+                        if (SCHEME == SMCB_RS_STRATIFIED) Cc.c1[r][q] = (on && hh + 1 < n) ? a.cdf[hh + 1] : 2.0;
+                    }
+                }
+            };
+            auto process = [&](int64_t p0, const Hints &H, const Cdf &Cc) {
+#ifdef SMCB_TRACE
+                const unsigned long long dbg_t1 = gtimer() + (unsigned long long)(Cc.c0[0][0] > 3.0);    // (after the loads)
+#endif
+                long long h[kR][2];
+                double su[kR][2];
+                bool valid[kR], two[kR], moved[kR];
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int64_t p = p0 + (int64_t)r * BS;
+                    moved[r] = false;
+                    valid[r] = p < pend;
+                    two[r] = valid[r] && (2 * p + 1 < n);
                     if (SCHEME == SMCB_RS_SYSTEMATIC) {                    // resampling.py:609
                         su[r][0] = (u_sys + (double)(2 * p)) / M_;
                         su[r][1] = (u_sys + (double)(2 * p + 1)) / M_;
@@ -1738,36 +1773,25 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
                         su[r][1] = (u1 + (double)(2 * p + 1)) / M_;
                     }
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {                    // the two CDF entries that decide the hint
-                        long long hh = h[r][q];
+                    for (int q = 0; q < 2; q++) {
+                        long long hh = H.h[r][q];
                         hh = hh < 0 ? 0 : (hh > n - 1 ? n - 1 : hh);
-                        moved[r] = moved[r] || hh != h[r][q];
+                        moved[r] = moved[r] || hh != H.h[r][q];
                         h[r][q] = hh;
-                        const bool on = q == 0 ? valid[r] : two[r];
-                        // (plain loads: this SM touches these lines for the first time in this launch, after the grid
-                        // barrier, so L1 cannot hold an older copy -- and neighbouring outputs reuse them)
-                        c0[r][q] = on ? a.cdf[hh] : 2.0;
-                        cm[r][q] = (on && hh > 0) ? a.cdf[hh - 1] : -1.0;
-                        // stratified: the hint answers k / N and su_k lies up to 1 / N further, so about half of the
-                        // outputs belong to the NEXT entry -- fetch it with the other two instead of walking
-                        if (SCHEME == SMCB_RS_STRATIFIED) c1[r][q] = (on && hh + 1 < n) ? a.cdf[hh + 1] : 2.0;
                     }
                 }
-#ifdef SMCB_TRACE
-                const unsigned long long dbg_t1 = gtimer() + (unsigned long long)(c0[0][0] > 3.0);    // (after the loads)
-#endif
 #pragma unroll
                 for (int r = 0; r < kR; r++) {
 #pragma unroll
                     for (int q = 0; q < 2; q++) {
                         const bool on = q == 0 ? valid[r] : two[r];
-                        bool ok = (cm[r][q] < su[r][q]) && (su[r][q] <= c0[r][q] || h[r][q] == n - 1);
+                        bool ok = (Cc.cm[r][q] < su[r][q]) && (su[r][q] <= Cc.c0[r][q] || h[r][q] == n - 1);
                         if (SCHEME == SMCB_RS_STRATIFIED) {
-                            if (on && !ok && c0[r][q] < su[r][q] && (su[r][q] <= c1[r][q] || h[r][q] + 1 == n - 1)) {
+                            if (on && !ok && Cc.c0[r][q] < su[r][q] && (su[r][q] <= Cc.c1[r][q] || h[r][q] + 1 == n - 1)) {
                                 h[r][q] += 1; moved[r] = true; ok = true;
                             }
                         }
-                        if (on && !ok && c0[r][q] < su[r][q] && h[r][q] + 1 < n) {
+                        if (on && !ok && Cc.c0[r][q] < su[r][q] && h[r][q] + 1 < n) {
                             // the hint is too low: ONE round trip for the next kWin entries (independent loads, mostly
                             // one line) instead of a chain of dependent ones; the search below only runs past them
                             constexpr int kWin = 6;
@@ -1809,8 +1833,33 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
                 }
 #ifdef SMCB_TRACE
                 const unsigned long long dbg_t3 = gtimer() + (unsigned long long)(acc.w.s < -1.0);
-                dbg_t[0] = max(dbg_t[0], dbg_t1 - dbg_t0); dbg_t[1] = max(dbg_t[1], dbg_t2 - dbg_t1); dbg_t[2] = max(dbg_t[2], dbg_t3 - dbg_t2);
+                dbg_t[1] = max(dbg_t[1], dbg_t2 - dbg_t1); dbg_t[2] = max(dbg_t[2], dbg_t3 - dbg_t2);
 #endif
+            };
+            constexpr int64_t kStep = (int64_t)kR * BS;
+            if (SMCB_RS_PIPE && D == 1) {
+                Hints h_cur, h_nxt;
+                Cdf c_cur;
+                int64_t p0 = pstart + threadIdx.x;
+                ld_hints(p0, h_cur);                                 // (all loaders mask pairs beyond pend themselves)
+                ld_hints(p0 + kStep, h_nxt);
+                ld_cdf(p0, h_cur, c_cur);
+                for (; p0 < pend; p0 += kStep) {
+                    Hints h_n2;
+                    Cdf c_nxt;
+                    ld_cdf(p0 + kStep, h_nxt, c_nxt);                // its hints were requested a round ago
+                    ld_hints(p0 + 2 * kStep, h_n2);
+                    process(p0, h_cur, c_cur);
+                    h_cur = h_nxt; c_cur = c_nxt; h_nxt = h_n2;
+                }
+            } else {
+                for (int64_t p0 = pstart + threadIdx.x; p0 < pend; p0 += kStep) {
+                    Hints H;
+                    Cdf Cc;
+                    ld_hints(p0, H);
+                    ld_cdf(p0, H, Cc);
+                    process(p0, H, Cc);
+                }
             }
 #ifdef SMCB_TRACE
             {   // per warp: end of its move loop | (settle calls << 32 | largest hint error) of the resampling step

@@ -239,6 +239,33 @@ class BearingsOnly(StateSpaceModel):
         return dists.Normal(loc=angle, scale=self.sigmaY)
 
 
+class MVStochVol(StateSpaceModel):
+    """state_space_models.py:633-654: X_0 ~ N(mu, covX), X_t - mu = F (X_{t-1} - mu) + U_t, Y_t(k) = exp(X_t(k) / 2)
+    V_t(k), V_t ~ N(0, corY).  The reference ships it without default parameters (``None``): pass mu (d,), covX,
+    corY, F (d, d).  Plugin path (MvNormal kernels with per-particle scale), d <= 32."""
+    default_params = {"mu": 0.0, "covX": None, "corY": None, "F": None}
+
+    def _dev(self, name):
+        key = "_dev_" + name
+        if key not in self.__dict__:
+            self.__dict__[key] = dists.as_device(np.asarray(getattr(self, name), dtype=np.float64))
+        return self.__dict__[key]
+
+    def offset(self):
+        return np.asarray(self.mu, dtype=np.float64) - np.dot(self.F, np.asarray(self.mu, dtype=np.float64))
+
+    def PX0(self):
+        return dists.MvNormal(loc=np.asarray(self.mu, dtype=np.float64), cov=self.covX)
+
+    def PX(self, t, xp):
+        if "_dev_off" not in self.__dict__:
+            self.__dict__["_dev_off"] = dists.as_device(np.broadcast_to(self.offset(), (np.asarray(self.F).shape[0],)).copy())
+        return dists.MvNormal(loc=xp @ self._dev("F").t() + self.__dict__["_dev_off"], cov=self.covX)
+
+    def PY(self, t, xp, x):
+        return dists.MvNormal(scale=torch.exp(0.5 * x), cov=self.corY)
+
+
 # ---------------------------------------------------------------------------
 # recogniser: Feynman-Kac object -> constants of the fused kernel
 # ---------------------------------------------------------------------------

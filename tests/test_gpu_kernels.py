@@ -479,3 +479,33 @@ def test_indepprod_dirac_vs_reference(pb, golden):
     np.testing.assert_allclose(host(law.logpdf(dev(xn))), g["d/indep/logpdf"], rtol=1e-13)
     lpy = host(ssm.BearingsOnly().PY(1, xp, dev(xn)).logpdf(np.array([0.7])))
     np.testing.assert_allclose(lpy, g["d/indep/bearing_logpdf"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_mvstochvol_plugin_path(pb):
+    """MVStochVol (state_space_models.py:633-654) on the plugin path: MvNormal kernels with a per-particle scale.
+    (1) its closures against the oracle's on the same particles; (2) logLt of bootstrap filters at N = 2000 within
+    3 sigma of 30 runs of the live reference (tests/golden/golden_mvsv.npz)."""
+    import os
+    import particles_b200
+    from particles_b200 import state_space_models as ssm
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_mvsv.npz"))
+    kw = dict(mu=g["mu"], covX=g["covX"], corY=g["corY"], F=g["F"])
+    m, mo = ssm.MVStochVol(**kw), orc.MVStochVol(**kw)
+    r = np.random.RandomState(4)
+    xp, x = r.randn(500, 3) * 0.5 - 0.4, r.randn(500, 3) * 0.5 - 0.4
+    np.testing.assert_allclose(host(m.PX(3, dev(xp)).logpdf(dev(x))), mo.PX(3, xp).logpdf(x), rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(host(m.PY(3, dev(xp), dev(x)).logpdf(dev(g["y"][3]))), mo.PY(3, xp, x).logpdf(g["y"][3]),
+                               rtol=1e-11, atol=1e-11)
+    z = r.randn(500, 3)
+    np.testing.assert_allclose(host(m.PX(3, dev(xp)).rvs(size=500, z=dev(z))), mo.PX(3, xp).rvs(500, z=z), rtol=1e-12, atol=1e-13)
+    data = [row.reshape(1, -1) for row in g["y"]]
+    lls = []
+    for seed in range(6):
+        pf = particles_b200.SMC(fk=ssm.Bootstrap(ssm=m, data=data), N=2000, seed=seed)
+        pf.run()
+        assert not pf.fused and pf.wgts.N == 2000
+        lls.append(pf.logLt)
+    ref = g["stat_logLt_N2000"]
+    sd = ref.std(ddof=1)
+    assert abs(np.mean(lls) - ref.mean()) < 3 * sd * np.sqrt(1 / 6 + 1 / len(ref)), (lls, ref.mean(), sd)
