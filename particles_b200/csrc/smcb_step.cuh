@@ -53,7 +53,7 @@ constexpr int kTailBlock = 256;     // threads of the one-CTA helper kernels (>=
 #define SMCB_SPECULATE 1         // sharded filters: start the streaming pass before the peers' statistics arrive
 #endif
 #ifndef SMCB_RS_PIPE
-#define SMCB_RS_PIPE 1             // resampling move pass of the 1-D models: hints two rounds ahead, CDF entries one
+#define SMCB_RS_PIPE 0             // resampling move pass of the 1-D models: hints two rounds ahead, CDF entries one
 #endif
 #ifndef SMCB_RS_KR
 #define SMCB_RS_KR 2             // resampling move pass: pairs in flight per thread
