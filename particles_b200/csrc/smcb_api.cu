@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(kBlock) k_lse(double *v, const double *__restr
     int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (MODE != kModeWeightedMean) {
         // eight independent loads in flight per thread and ONE running-max update per batch of eight (one exp per
-        // value, branch-free polynomial exp): the scalar loop with a library exp and a rescale test per value ran
-        // at a quarter of the HBM rate
+        // value, branch-free polynomial exp).  Measured: 51 -> 43 us for 80 MB; ncu (profiles/r02_standalone_ncu_summary.json)
+        // shows 71 instructions per value and the fp64 pipe 53 % active, but a table-assisted exp with a third of the
+        // instructions did not move the time (45 us): the kernel is bound by the latency of its four rounds of loads per
+        // thread, not by issue
         bool saw_nan = false;
         for (; i + 7 * stride < n; i += 8 * stride) {
             double x[8];
@@ -480,7 +482,16 @@ static int run_scan(smcb_ctx *c, const LOAD &load, int64_t n, T *out, int slot =
         SMCB_CUDA(cudaGetLastError());
         return SMCB_OK;
     }
-    const int64_t want = 148 * 6;                                  // chunks: a few CTAs per SM, <= kScanMaxChunks
+    // one chunk per CTA that can be resident (occupancy of the scan kernel x SMs): a grid of 1.1 - 1.4 waves, as the
+    // fixed "6 per SM" gave, ends with a half-empty second round
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_scan_chunks<T, LOAD>, kBlock, 0) != cudaSuccess || o < 1) o = 4;
+        occ = o;
+    }
+    int64_t want = (int64_t)kSMs * occ;
+    if (want > kScanMaxChunks) want = kScanMaxChunks;
     const int tpc = (int)((tiles + want - 1) / want);
     const int nchunks = (int)((tiles + tpc - 1) / tpc);
     T *sums = reinterpret_cast<T *>(st.agg);                       // the slot's tile-state area doubles as the chunk sums
@@ -586,7 +597,14 @@ static int run_search(smcb_ctx *c, const double *cdf, int64_t n, const SU &su, i
     if (rc) return rc;
     int64_t *bnd = reinterpret_cast<int64_t *>((char *)c->ws + base);
     k_search_bounds<SU><<<(int)((tiles + 1 + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(cdf, n, su, m, tiles, bnd);
-    int grid = (int)(tiles < kMaxGrid ? tiles : kMaxGrid);
+    static int occ = 0;                        // resident CTAs per SM of this instantiation: the grid is ONE full wave
+    if (occ == 0) {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_search<SU>, kBlock, 0) != cudaSuccess || o < 1) o = 4;
+        occ = o;
+    }
+    const int64_t wave = (int64_t)kSMs * occ;
+    int grid = (int)(tiles < wave ? tiles : wave);
     k_search<SU><<<grid, kBlock, 0, c->stream>>>(cdf, n, su, m, A, a_offset, bnd);
     c->launches += 2;
     SMCB_CUDA(cudaGetLastError());

@@ -252,11 +252,15 @@ __device__ __forceinline__ void scan_chunks(const LOAD &load, int64_t n, int til
     __syncthreads();
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_chunk;
     T carry = 0;
+    T nxt[kScanItems];                                   // the next tile's values are requested before this one is scanned
+    if (t0 * kScanTile < n) load(t0 * kScanTile + (int64_t)tid * kScanItems, n, nxt);
     for (int k = 0; k < tiles_per_chunk; k++) {
         if ((t0 + k) * kScanTile >= n) break;
         const int64_t i0 = (t0 + k) * kScanTile + (int64_t)tid * kScanItems;
         T r[kScanItems];
-        load(i0, n, r);
+#pragma unroll
+        for (int j = 0; j < kScanItems; j++) r[j] = nxt[j];
+        if (k + 1 < tiles_per_chunk && (t0 + k + 1) * kScanTile < n) load(i0 + kScanTile, n, nxt);
 #pragma unroll
         for (int j = 1; j < kScanItems; j++) r[j] = r[j - 1] + r[j];
         const T iw = warp_scan_monotone(r[kScanItems - 1], lane);

@@ -389,13 +389,14 @@ ND_CASES = [("bearings", "boot", "stratified"), ("mvlg", "boot", "stratified"),
             ("mvlg", "guided", "systematic"), ("mvlg", "apf", "stratified"), ("mvlg", "auxboot", "multinomial")]
 
 
+@pytest.mark.parametrize("N", [2000, 2001])
 @pytest.mark.parametrize("mname,fkname,scheme", ND_CASES)
-def test_fused_nd_step_by_step_vs_oracle(golden, mname, fkname, scheme):
+def test_fused_nd_step_by_step_vs_oracle(golden, mname, fkname, scheme, N):
     """Fused d-dimensional kernels (SoA state, d = 4) with injected normals / uniforms against the
-    oracle: same ancestors, particles / weights / logLt to fp64 round-off."""
+    oracle: same ancestors, particles / weights / logLt to fp64 round-off.  N odd: the SoA component rows are then
+    only 8-byte aligned and the kernels must take their scalar load / store path."""
     import particles_b200 as pb
     from particles_b200 import kalman, state_space_models as ssm
-    N = 2000
     if mname == "bearings":
         dev_m, orc_m, nz = ssm.BearingsOnly(), orc.BearingsOnly(), 2
         y = list(golden["data/bearings_seed0_T40"].reshape(-1, 1))
