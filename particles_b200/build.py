@@ -29,13 +29,35 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+STAMP = SO + ".srchash"
+
+
+def _deps():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc"))) + [
+        os.path.join(HERE, "..", "include", "smcb.h")]
+
+
+def source_hash():
+    """Content hash of everything the library is compiled from (+ the flags): the stamp written next to the .so."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
+    """Stale if the .so is missing, if the content stamp written by the last build differs from the sources (an edit
+    made WHILE a build was running leaves the .so newer than the file it no longer matches), or -- without a stamp --
+    if any source is newer than the .so."""
     if not os.path.exists(SO):
         return True
+    if os.path.exists(STAMP):
+        return open(STAMP).read().strip() != source_hash()
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(HERE, "..", "include", "smcb.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force=False, verbose=False, extra=None, out=None):
@@ -48,6 +70,7 @@ def build(force=False, verbose=False, extra=None, out=None):
     if not variant and not force and not needs_build():
         return SO
     nvcc = _nvcc()
+    stamp = source_hash()                 # of the sources as they are NOW, before the compilers read them
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra)
     tag = ".variant" if variant else ""
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
@@ -64,8 +87,16 @@ def build(force=False, verbose=False, extra=None, out=None):
         objs = list(pool.map(compile_one, SOURCES))
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out]
                           + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    if not variant:
+        with open(STAMP, "w") as f:
+            f.write(stamp + "\n")
     return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--stamp" in sys.argv:             # declare the existing .so current (it was built from exactly these sources)
+        with open(STAMP, "w") as f:
+            f.write(source_hash() + "\n")
+        print(STAMP)
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
