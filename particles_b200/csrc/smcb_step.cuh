@@ -1272,7 +1272,8 @@ __global__ void __launch_bounds__(StepCfg<M>::BS, 1) k_step(M model, FilterArgs 
     StepDecision dec;
     dec.rs = 0; dec.nrs_prev = 0; dec.reset_c = 0.0; dec.xm = 0.0; dec.xs = 1.0; dec.p_b = 0.0; dec.p_next = 0.0;
     if (!speculate) dec = prologue_end<APF, BS>(a, t, sh, blockIdx.x == 0, true, pc);
-    else __syncthreads();
+    // (no block barrier on the speculative path: CTA 0's sending lanes sit in their system-scope fence for a few
+    // microseconds, and the other warps of that CTA start on the slabs meanwhile -- the dynamic slab schedule absorbs it)
     mbar_wait(&s_tabbar, 0);                           // (the prologue's barriers made the init visible)
     SMCB_TRACE_MARK(2);
     const int cur = (int)((t - 1) & 1);                // step s writes buffers [s & 1]
