@@ -148,7 +148,7 @@ def lse3_of(v):
 
 def shard_shares(aux_triples):
     """Global resampling: shard r owns [goff[r], goff[r+1]) of the global CDF, gpi[r] = its share of the
-    total (auxiliary) weight mass -- what ``k_finish`` derives from the exchanged statistics (rank order,
+    total (auxiliary) weight mass -- what the step kernel's prologue derives from the exchanged statistics (rank order,
     sequential sums, so every rank holds the same bits)."""
     M, S, _ = merge_lse3(aux_triples)
     gpi = np.array([0.0 if m == -np.inf else s * np.exp(m - M) / S for (m, s, _q) in aux_triples])
@@ -159,7 +159,7 @@ def shard_shares(aux_triples):
 
 
 def global_ancestors(su, goff, gpi, local_cdfs):
-    """Two-level inverse CDF of ``k_resample_global``: grid point ``su`` -> shard k with
+    """Two-level inverse CDF of the step kernel's global resampling branch: grid point ``su`` -> shard k with
     goff[k] <= su < goff[k+1] (empty shards skipped) -> position of (su - goff[k]) / gpi[k] in shard k's own
     normalised CDF.  Returns GLOBAL particle indices k * n + a."""
     su = np.asarray(su, dtype=np.float64)
